@@ -1,0 +1,28 @@
+"""B200-native Chamfer / density-aware Chamfer (DCD) hot path of U-RED.
+
+Drop-in surface (same names and signatures as the reference):
+    chamfer_3DDist()(x, y) -> (dist1, dist2, idx1, idx2)
+    calc_dcd(x, gt, alpha=1000, n_lambda=1, return_raw=False, non_reg=False)
+    calc_cd(output, gt, calc_f1=False, return_raw=False, normalize=False, separate=False)
+    cd, fscore                      (Density_aware_Chamfer_Distance/utils_v2/metrics/__init__.py)
+    ChamferLoss, chamfer_distance2, compute_cm_loss      (loss/chamfer_loss.py)
+plus the batched retrieval API in .retrieval.  Everything runs on the hand-written sm_100a
+kernels behind include/ured_chamfer.h; there is no CPU, PyTorch or Triton fallback.
+"""
+from . import _native
+from ._native import NativeLibraryError, build_native
+from .dist_chamfer_3D import chamfer_3DDist, chamfer_3DFunction, nn_forward, nn_backward
+from .dist_chamfer_3D import chamfer_3DDist as cd
+from .model_utils import calc_cd, calc_dcd, fscore
+from .chamfer_loss import ChamferLoss, chamfer_distance2, compute_cm_loss
+from . import retrieval
+from .retrieval import (PackedClouds, score_candidates, score_library, topk_smallest, retrieve,
+                        retrieve_sharded, shard_bounds, merge_topk, gather_and_merge)
+
+__all__ = [
+    "chamfer_3DDist", "chamfer_3DFunction", "nn_forward", "nn_backward", "cd", "fscore", "calc_cd", "calc_dcd",
+    "ChamferLoss", "chamfer_distance2", "compute_cm_loss",
+    "PackedClouds", "score_candidates", "score_library", "topk_smallest", "retrieve",
+    "retrieve_sharded", "shard_bounds", "merge_topk", "gather_and_merge",
+    "NativeLibraryError", "build_native",
+]

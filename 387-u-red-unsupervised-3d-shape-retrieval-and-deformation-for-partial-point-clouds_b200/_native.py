@@ -1,0 +1,123 @@
+"""ctypes binding of the C-ABI library (include/ured_chamfer.h).
+
+This is the only place the package touches native code.  There is NO CPU fallback and no
+alternative backend: if ``libured_chamfer.so`` is missing or a call fails, the caller gets an
+exception (the reference silently ignores its op's return value, dist_chamfer_3D.py:45).
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libured_chamfer.so")
+SRC_PATH = os.path.join(_HERE, "csrc", "ured_chamfer.cu")
+INCLUDE_DIR = os.path.join(_ROOT, "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+URED_FLAG_EXACT_ONLY = 1
+
+_c_float_p = ctypes.c_void_p  # device pointers travel as integers
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "ured_abi_version": (ctypes.c_int, []),
+    "ured_last_error_string": (ctypes.c_char_p, []),
+    "ured_packed_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "ured_pack_clouds": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "ured_nn_packed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_uint, ctypes.c_void_p]),
+    "ured_chamfer_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "ured_chamfer_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint, ctypes.c_void_p]),
+    "ured_chamfer_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "ured_dcd_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "ured_dcd_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "ured_topk_smallest": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NativeLibraryError(RuntimeError):
+    """The CUDA extension is missing, cannot be loaded, or a call into it failed."""
+
+
+def build_native(verbose=False):
+    """Compile csrc/ured_chamfer.cu for sm_100a into libured_chamfer.so (in-tree)."""
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-I", INCLUDE_DIR, "-o", LIB_PATH, SRC_PATH]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise NativeLibraryError("nvcc failed:\n" + res.stdout + res.stderr)
+    global _lib
+    with _lock:
+        _lib = None
+    return res.stderr if verbose else LIB_PATH
+
+
+def load():
+    """Load the library once; raises NativeLibraryError if it is absent (never falls back)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). This package has no CPU or PyTorch fallback.")
+        try:
+            lib = ctypes.CDLL(LIB_PATH)
+        except OSError as exc:  # pragma: no cover - depends on the host
+            raise NativeLibraryError(f"cannot load {LIB_PATH}: {exc}") from exc
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as exc:
+                raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from exc
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.ured_abi_version() != 1:
+            raise NativeLibraryError("ABI version mismatch between ured_chamfer.h and the built library")
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    """Turn a non-zero C-ABI return code into an exception."""
+    if rc != 0:
+        msg = load().ured_last_error_string().decode("utf-8", "replace")
+        raise NativeLibraryError(f"{what} failed with code {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())

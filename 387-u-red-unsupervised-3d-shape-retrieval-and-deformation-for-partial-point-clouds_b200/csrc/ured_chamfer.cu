@@ -1,0 +1,714 @@
+// ured_chamfer.cu -- B200 (sm_100a) kernels and C ABI for the Chamfer / DCD hot path.
+//
+// Replaces, for this one path, the reference's native op and the torch-op epilogue on top of it
+// (paths relative to the reference tree, DCD/ = Density_aware_Chamfer_Distance/):
+//   NmDistanceKernel / chamfer_cuda_forward        DCD/utils_v2/metrics/CD/chamfer3D/chamfer3D.cu:12-154
+//   NmDistanceGradKernel / chamfer_cuda_backward   DCD/utils_v2/metrics/CD/chamfer3D/chamfer3D.cu:155-195
+//   calc_cd / calc_dcd torch-op body               DCD/utils_v2/model_utils.py:13-70
+//   torch.topk(cd_m, k, largest=False)             dataset/dataset_utils.py:1043-1051
+// The declarations and the contract of every entry point live in include/ured_chamfer.h.
+//
+// Kernel plan (DESIGN.md has the numbers):
+//   pack_kernel   xyz[count,n,3] -> padded SoA image X|Y|Z|W (+ max W per cloud)     HBM-bound, tiny
+//   nn_kernel     both directions of the nearest-neighbour search in ONE launch.  Each CTA owns
+//                 T*R query points of one (pair, direction), streams the opposing cloud through
+//                 shared memory with TMA bulk copies (cp.async.bulk + mbarrier, 2 stages) and
+//                 evaluates packed FP32 math (FADD2/FMUL2/FFMA2) with a register-resident chunk
+//                 minimum (FMNMX3).  Two variants:
+//                   EXACT   difference form d = fma(dz,dz,fma(dx,dx,dy*dy)) on every pair
+//                           (the reference arithmetic, 6 FP32-pipe ops per pair);
+//                   SCREEN  3-FFMA expansion form s = |c|^2 - 2 q.c as a filter, then the exact
+//                           difference form only on the winning 16-candidate chunk; queries whose
+//                           runner-up chunk is within a rigorous rounding bound of the winner are
+//                           re-scanned exactly by their warp.  Output bits are identical.
+//   dcd_fwd_kernel   per pair: shared-memory histograms of idx1/idx2, weights, loss/cd_p/cd_t
+//   grad_*_kernel    gather + atomic scatter of the Chamfer backward, fused with the DCD chain rule
+//   topk_kernel      k smallest (score, index) per row
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "ured_chamfer.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+thread_local char g_err[256] = "no error";
+
+int fail_arg(int code, const char *what) {
+    snprintf(g_err, sizeof(g_err), "ured_chamfer: %s", what);
+    return code;
+}
+int check_cuda(cudaError_t e, const char *where) {
+    if (e == cudaSuccess) return 0;
+    snprintf(g_err, sizeof(g_err), "ured_chamfer: %s: %s", where, cudaGetErrorString(e));
+    return (int)e;
+}
+#define URED_CUDA(call, where)                       \
+    do {                                             \
+        int rc_ = check_cuda((call), (where));       \
+        if (rc_) return rc_;                         \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int pad32(int n) { return (n + 31) / 32 * 32; }
+
+// ------------------------------------------------------------------------------------------
+// packed cloud image
+// ------------------------------------------------------------------------------------------
+constexpr int kPackThreads = 256;
+
+// one CTA per cloud; writes X|Y|Z|W (each np floats) and max W
+__global__ void __launch_bounds__(kPackThreads) pack_kernel(const float *__restrict__ xyz, int n, int np,
+                                                            float *__restrict__ soa, float *__restrict__ wmax) {
+    const size_t cloud = blockIdx.x;
+    const float *src = xyz + cloud * (size_t)n * 3;
+    float *X = soa + cloud * (size_t)np * 4;
+    float *Y = X + np, *Z = Y + np, *W = Z + np;
+    float m = 0.0f;
+    for (int k = threadIdx.x; k < np; k += kPackThreads) {
+        int ks = k < n ? k : n - 1;  // padding replicates the last point: it can tie with it, never beat it
+        float x = src[ks * 3 + 0], y = src[ks * 3 + 1], z = src[ks * 3 + 2];
+        float w = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+        X[k] = x; Y[k] = y; Z[k] = z; W[k] = w;
+        m = fmaxf(m, w);          // fmaxf drops NaN; non-finite inputs are outside the screening contract anyway
+        if (!(w <= 3.0e38f)) m = __int_as_float(0x7f800000);  // inf/NaN norm: force the exact path
+    }
+    __shared__ float red[kPackThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < kPackThreads / 32; i++) m = fmaxf(m, red[i]);
+        wmax[cloud] = m;
+    }
+}
+
+struct PackedView {
+    const float *soa;   // count * 4 * np floats
+    const float *wmax;  // count floats
+    int np;
+};
+PackedView view_packed(const void *packed, int count, int n) {
+    PackedView v;
+    v.np = pad32(n);
+    v.soa = (const float *)packed;
+    v.wmax = (const float *)((const char *)packed + align_up((size_t)count * 4 * v.np * sizeof(float), 256));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA / mbarrier helpers (PTX; SASS shows UBLKCP + SYNCS)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// nearest-neighbour kernel
+// ------------------------------------------------------------------------------------------
+constexpr int kNNThreads = 128;  // 4 warps, one per SM sub-partition; 5-6 CTAs resident per SM
+constexpr int kTile = 1024;      // candidates per shared-memory stage
+constexpr int kStages = 2;
+constexpr int kChunk = 16;       // candidates per running-minimum chunk (divides 32)
+constexpr float kInf = __builtin_huge_valf();
+
+struct NNParams {
+    const float *xyz[2];   // raw clouds (queries are read from here)
+    const float *soa[2];   // packed images (candidates are streamed from here)
+    const float *wmax[2];  // max |p|^2 per cloud
+    float *dist[2];
+    int *idx[2];
+    int n[2];
+    int np[2];
+    int qtiles[2];  // query tiles per pair for direction 0 / 1
+    int rep1, mod2;
+};
+
+// the reference's pair arithmetic (chamfer3D.cu:32-35 as compiled by nvcc 12.9 for sm_100a):
+// differences are candidate - query, d = fma(dz,dz, fma(dx,dx, dy*dy))
+__device__ __forceinline__ float exact_d(float cx, float cy, float cz, float qx, float qy, float qz) {
+    float dx = __fsub_rn(cx, qx), dy = __fsub_rn(cy, qy), dz = __fsub_rn(cz, qz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+template <bool SCREEN, int R>
+__global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
+    constexpr int NARR = SCREEN ? 4 : 3;
+    constexpr int G = kChunk;
+    extern __shared__ __align__(128) float stage_mem[];  // kStages * NARR * kTile floats
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+
+    const int tid = threadIdx.x;
+    // ---- work item: (pair b, direction, query tile) --------------------------------------
+    const int per_pair = p.qtiles[0] + p.qtiles[1];
+    const int b = blockIdx.x / per_pair;
+    const int rem = blockIdx.x - b * per_pair;
+    const int dir = rem >= p.qtiles[0] ? 1 : 0;
+    const int qt = dir ? rem - p.qtiles[0] : rem;
+    const int c1 = b / p.rep1, c2 = b % p.mod2;
+    const int cq = dir ? c2 : c1, cc = dir ? c1 : c2;
+    // (ternaries, not p.x[dir]: dynamic indexing would copy the parameter block to local memory)
+    const int nq = dir ? p.n[1] : p.n[0], nc = dir ? p.n[0] : p.n[1], ncp = dir ? p.np[0] : p.np[1];
+    const float *__restrict__ qxyz = (dir ? p.xyz[1] : p.xyz[0]) + (size_t)cq * nq * 3;
+    const float *__restrict__ csoa = (dir ? p.soa[0] : p.soa[1]) + (size_t)cc * ncp * 4;
+
+    // ---- pipeline prologue ---------------------------------------------------------------
+    const int ntiles = (ncp + kTile - 1) / kTile;
+    auto issue_tile = [&](int t) {
+        const int s = t % kStages;
+        const int k0 = t * kTile;
+        const int tk = min(kTile, ncp - k0);
+        const uint32_t bytes = (uint32_t)tk * sizeof(float);
+        mbar_arrive_expect_tx(&full_bar[s], bytes * NARR);
+#pragma unroll
+        for (int a = 0; a < NARR; a++)
+            tma_bulk_g2s(stage_mem + (s * NARR + a) * kTile, csoa + (size_t)a * ncp + k0, bytes, &full_bar[s]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; s++) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        issue_tile(0);
+        if (ntiles > 1) issue_tile(1);
+    }
+
+    // ---- queries in registers ------------------------------------------------------------
+    float qx[R], qy[R], qz[R];   // EXACT: -q (added to the candidate); SCREEN: -2q (multiplied)
+    float oqx[R], oqy[R], oqz[R];
+    float best[R], second[R];
+    int bchunk[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        int j = (qt * R + r) * kNNThreads + tid;
+        j = j < nq ? j : nq - 1;
+        oqx[r] = qxyz[j * 3 + 0]; oqy[r] = qxyz[j * 3 + 1]; oqz[r] = qxyz[j * 3 + 2];
+        const float sc = SCREEN ? -2.0f : -1.0f;
+        qx[r] = sc * oqx[r]; qy[r] = sc * oqy[r]; qz[r] = sc * oqz[r];
+        best[r] = kInf; second[r] = kInf; bchunk[r] = 0;
+    }
+
+    // ---- main loop over candidate tiles ----------------------------------------------------
+    for (int t = 0; t < ntiles; t++) {
+        const int s = t % kStages;
+        const int k0 = t * kTile;
+        const int tk = min(kTile, ncp - k0);
+        mbar_wait(&full_bar[s], (uint32_t)(t / kStages) & 1u);
+        const float *X = stage_mem + (s * NARR + 0) * kTile;
+        const float *Y = stage_mem + (s * NARR + 1) * kTile;
+        const float *Z = stage_mem + (s * NARR + 2) * kTile;
+        const float *W = stage_mem + (s * NARR + (SCREEN ? 3 : 2)) * kTile;
+
+        for (int c0 = 0; c0 < tk; c0 += G) {
+            float cm[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) cm[r] = kInf;
+#pragma unroll
+            for (int k = 0; k < G; k += 4) {
+                const float4 x4 = *reinterpret_cast<const float4 *>(X + c0 + k);
+                const float4 y4 = *reinterpret_cast<const float4 *>(Y + c0 + k);
+                const float4 z4 = *reinterpret_cast<const float4 *>(Z + c0 + k);
+                if (SCREEN) {
+                    const float4 w4 = *reinterpret_cast<const float4 *>(W + c0 + k);
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const float2 bx = make_float2(qx[r], qx[r]), by = make_float2(qy[r], qy[r]), bz = make_float2(qz[r], qz[r]);
+                        float2 t0 = __ffma2_rn(make_float2(z4.x, z4.y), bz, make_float2(w4.x, w4.y));
+                        float2 t1 = __ffma2_rn(make_float2(z4.z, z4.w), bz, make_float2(w4.z, w4.w));
+                        t0 = __ffma2_rn(make_float2(y4.x, y4.y), by, t0);
+                        t1 = __ffma2_rn(make_float2(y4.z, y4.w), by, t1);
+                        t0 = __ffma2_rn(make_float2(x4.x, x4.y), bx, t0);
+                        t1 = __ffma2_rn(make_float2(x4.z, x4.w), bx, t1);
+                        cm[r] = fminf(fminf(cm[r], t0.x), t0.y);
+                        cm[r] = fminf(fminf(cm[r], t1.x), t1.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const float2 bx = make_float2(qx[r], qx[r]), by = make_float2(qy[r], qy[r]), bz = make_float2(qz[r], qz[r]);
+                        const float2 dx0 = __fadd2_rn(make_float2(x4.x, x4.y), bx), dx1 = __fadd2_rn(make_float2(x4.z, x4.w), bx);
+                        const float2 dy0 = __fadd2_rn(make_float2(y4.x, y4.y), by), dy1 = __fadd2_rn(make_float2(y4.z, y4.w), by);
+                        const float2 dz0 = __fadd2_rn(make_float2(z4.x, z4.y), bz), dz1 = __fadd2_rn(make_float2(z4.z, z4.w), bz);
+                        float2 t0 = __fmul2_rn(dy0, dy0), t1 = __fmul2_rn(dy1, dy1);
+                        t0 = __ffma2_rn(dx0, dx0, t0);
+                        t1 = __ffma2_rn(dx1, dx1, t1);
+                        t0 = __ffma2_rn(dz0, dz0, t0);
+                        t1 = __ffma2_rn(dz1, dz1, t1);
+                        cm[r] = fminf(fminf(cm[r], t0.x), t0.y);
+                        cm[r] = fminf(fminf(cm[r], t1.x), t1.y);
+                    }
+                }
+            }
+            // chunk bookkeeping: strict '<' in ascending chunk order keeps the FIRST chunk holding the minimum
+            const int chunk_id = k0 + c0;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const bool better = cm[r] < best[r];
+                if (SCREEN) second[r] = fminf(second[r], fmaxf(cm[r], best[r]));
+                best[r] = fminf(best[r], cm[r]);
+                bchunk[r] = better ? chunk_id : bchunk[r];
+            }
+        }
+        __syncthreads();  // every thread is done with stage s
+        if (tid == 0 && t + kStages < ntiles) issue_tile(t + kStages);
+    }
+
+    // ---- exact resolution of the winning chunk ---------------------------------------------
+    const float *__restrict__ gX = csoa, *__restrict__ gY = csoa + ncp, *__restrict__ gZ = csoa + 2 * (size_t)ncp;
+    float cn = 0.0f;
+    if (SCREEN) cn = __fsqrt_ru((dir ? p.wmax[0] : p.wmax[1])[cc]) * 1.000001f;
+    const int lane = tid & 31;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int c = bchunk[r];
+        float bd = 0.0f;
+        int bi = c;
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            // entries past nc replicate point nc-1 and can therefore never be strictly smaller
+            const float d = exact_d(gX[c + k], gY[c + k], gZ[c + k], oqx[r], oqy[r], oqz[r]);
+            if (k == 0 || d < bd) { bd = d; bi = c + k; }
+        }
+        if (SCREEN) {
+            // |s + |q|^2 - d_fp32| <= 11.02 u S^2 with S = |q| + max|c| (DESIGN.md "screening bound");
+            // a runner-up chunk farther than twice that cannot hold the argmin.  eps = 32 u S^2.
+            const float qn = __fsqrt_ru(__fmaf_rn(oqz[r], oqz[r], __fmaf_rn(oqy[r], oqy[r], oqx[r] * oqx[r]))) * 1.000001f;
+            const float S = qn + cn;
+            const float eps = __fmaf_rn(S * S, 1.9073486e-6f /* 2^-19 */, 1e-35f);
+            const bool ambiguous = !(second[r] > best[r] + eps);
+            unsigned todo = __ballot_sync(0xffffffffu, ambiguous);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float ax = __shfl_sync(0xffffffffu, oqx[r], src);
+                const float ay = __shfl_sync(0xffffffffu, oqy[r], src);
+                const float az = __shfl_sync(0xffffffffu, oqz[r], src);
+                float wd = kInf;
+                int wi = 0x7fffffff;
+                for (int k = lane; k < nc; k += 32) {
+                    const float d = exact_d(gX[k], gY[k], gZ[k], ax, ay, az);
+                    if (d < wd || wi == 0x7fffffff) { wd = d; wi = k; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float od = __shfl_xor_sync(0xffffffffu, wd, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                    if (oi != 0x7fffffff && (wi == 0x7fffffff || od < wd || (od == wd && oi < wi))) { wd = od; wi = oi; }
+                }
+                if (lane == src) { bd = wd; bi = wi; }
+            }
+        }
+        const int j = (qt * R + r) * kNNThreads + tid;
+        if (j < nq) {
+            (dir ? p.dist[1] : p.dist[0])[(size_t)b * nq + j] = bd;
+            (dir ? p.idx[1] : p.idx[0])[(size_t)b * nq + j] = bi;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// DCD / CD epilogue
+// ------------------------------------------------------------------------------------------
+constexpr int kDcdThreads = 512;
+
+__device__ __forceinline__ double block_sum(double v, double *red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < kDcdThreads / 32; i++) s += red[i];  // fixed order: deterministic
+    return s;
+}
+
+// torch's pow(tensor, python scalar) special cases (ATen pow_tensor_scalar): 1 -> x, 2 -> x*x,
+// 0.5 -> sqrt, 0 -> 1; anything else goes through powf
+__device__ __forceinline__ float pow_lambda(float c, float n_lambda) {
+    if (n_lambda == 1.0f) return c;
+    if (n_lambda == 0.5f) return sqrtf(c);
+    if (n_lambda == 2.0f) return c * c;
+    if (n_lambda == 0.0f) return 1.0f;
+    return powf(c, n_lambda);
+}
+
+// one CTA per pair: shared-memory histograms of idx1 (bins = points of cloud 2) and idx2
+__global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__restrict__ dist1, const float *__restrict__ dist2,
+                                                              const int *__restrict__ idx1, const int *__restrict__ idx2,
+                                                              int n1, int n2, float alpha, float n_lambda, float frac_12,
+                                                              float frac_21, float *__restrict__ loss, float *__restrict__ cd_p,
+                                                              float *__restrict__ cd_t, float *__restrict__ ew1,
+                                                              float *__restrict__ ew2) {
+    extern __shared__ int hist[];  // count1[n2] | count2[n1]
+    __shared__ double red[kDcdThreads / 32];
+    int *count1 = hist, *count2 = hist + n2;
+    const size_t b = blockIdx.x;
+    const float *d1 = dist1 + b * n1, *d2 = dist2 + b * n2;
+    const int *i1 = idx1 + b * n1, *i2 = idx2 + b * n2;
+    for (int k = threadIdx.x; k < n1 + n2; k += kDcdThreads) hist[k] = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n1; k += kDcdThreads) atomicAdd(&count1[i1[k]], 1);
+    for (int k = threadIdx.x; k < n2; k += kDcdThreads) atomicAdd(&count2[i2[k]], 1);
+    __syncthreads();
+
+    double s_term[2], s_d[2], s_sqrt[2];
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int n = side ? n2 : n1;
+        const float *d = side ? d2 : d1;
+        const int *ix = side ? i2 : i1;
+        const int *cnt = side ? count2 : count1;
+        const float frac = side ? frac_12 : frac_21;
+        float *ew = side ? ew2 : ew1;
+        double a_term = 0.0, a_d = 0.0, a_sqrt = 0.0;
+        for (int k = threadIdx.x; k < n; k += kDcdThreads) {
+            const float dk = d[k];
+            const float c = (float)cnt[ix[k]];
+            // model_utils.py:31,35-37: exp(-d*alpha); (count**lambda + 1e-6)**(-1) * frac
+            const float e = expf(__fmul_rn(-dk, alpha));
+            const float w = __fmul_rn(__fdiv_rn(1.0f, __fadd_rn(pow_lambda(c, n_lambda), 1e-6f)), frac);
+            const float ewk = __fmul_rn(e, w);
+            if (ew) ew[b * n + k] = ewk;
+            a_term += (double)__fsub_rn(1.0f, ewk);
+            a_d += (double)dk;
+            a_sqrt += (double)sqrtf(dk);
+        }
+        s_term[side] = block_sum(a_term, red);
+        s_d[side] = block_sum(a_d, red);
+        s_sqrt[side] = block_sum(a_sqrt, red);
+    }
+    if (threadIdx.x == 0) {
+        const float loss1 = (float)(s_term[0] / n1), loss2 = (float)(s_term[1] / n2);
+        const float m1 = (float)(s_d[0] / n1), m2 = (float)(s_d[1] / n2);
+        const float r1 = (float)(s_sqrt[0] / n1), r2 = (float)(s_sqrt[1] / n2);
+        if (loss) loss[b] = (loss1 + loss2) / 2.0f;  // model_utils.py:45
+        if (cd_p) cd_p[b] = (r1 + r2) / 2.0f;        // model_utils.py:57
+        if (cd_t) cd_t[b] = m1 + m2;                 // model_utils.py:58
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: chamfer3D.cu:155-174 with the d(out)/d(dist) coefficient built in place
+// ------------------------------------------------------------------------------------------
+constexpr int kGradThreads = 256;
+
+struct GradParams {
+    const float *xyz[2];
+    const float *dist[2];
+    const int *idx[2];
+    const float *ew[2];
+    const float *g_dist[2];
+    const float *g_loss, *g_cd_p, *g_cd_t;
+    float *grad[2];
+    int n[2];
+    int rep1, mod2;
+    float alpha;
+};
+
+// PHASE 0: own-side terms, plain coalesced stores (every output element is written exactly once
+//          when rep1 == 1 / mod2 == B; broadcast clouds fall back to atomics on a zeroed buffer)
+// PHASE 1: scatter-side terms, red.global.add.f32 keyed on idx
+template <int PHASE, bool SHARED1, bool SHARED2>
+__global__ void __launch_bounds__(kGradThreads) grad_kernel(const GradParams p) {
+    const int per_pair = p.n[0] + p.n[1];
+    const size_t b = blockIdx.y;
+    for (int t = blockIdx.x * kGradThreads + threadIdx.x; t < per_pair; t += gridDim.x * kGradThreads) {
+        const int side = t >= p.n[0] ? 1 : 0;
+        const int j = side ? t - p.n[0] : t;
+        const int n_own = side ? p.n[1] : p.n[0], n_oth = side ? p.n[0] : p.n[1];
+        const size_t c1 = b / p.rep1, c2 = b % p.mod2;
+        const size_t c_own = side ? c2 : c1, c_oth = side ? c1 : c2;
+        const size_t pt = b * n_own + j;
+        // upstream gradient w.r.t. this point's squared NN distance
+        const float *g_dist = side ? p.g_dist[1] : p.g_dist[0];
+        float gd = g_dist ? g_dist[pt] : 0.0f;
+        if (p.g_cd_t) gd += p.g_cd_t[b] / (float)n_own;
+        if (p.g_cd_p) gd += p.g_cd_p[b] * 0.5f / (float)n_own * (0.5f / sqrtf((side ? p.dist[1] : p.dist[0])[pt]));
+        if (p.g_loss) gd += p.g_loss[b] * 0.5f / (float)n_own * (p.alpha * (side ? p.ew[1] : p.ew[0])[pt]);
+        const int j2 = (side ? p.idx[1] : p.idx[0])[pt];
+        const float *a = (side ? p.xyz[1] : p.xyz[0]) + (c_own * n_own + j) * 3;
+        const float *o = (side ? p.xyz[0] : p.xyz[1]) + (c_oth * n_oth + j2) * 3;
+        const float g = __fmul_rn(gd, 2.0f);  // chamfer3D.cu:166
+        const float gx = __fmul_rn(g, __fsub_rn(a[0], o[0]));
+        const float gy = __fmul_rn(g, __fsub_rn(a[1], o[1]));
+        const float gz = __fmul_rn(g, __fsub_rn(a[2], o[2]));
+        if (PHASE == 0) {
+            float *dst = (side ? p.grad[1] : p.grad[0]) + (c_own * n_own + j) * 3;
+            const bool shared_own = side ? SHARED2 : SHARED1;
+            if (shared_own) {
+                atomicAdd(dst + 0, gx); atomicAdd(dst + 1, gy); atomicAdd(dst + 2, gz);
+            } else {
+                dst[0] = gx; dst[1] = gy; dst[2] = gz;
+            }
+        } else {
+            float *dst = (side ? p.grad[0] : p.grad[1]) + (c_oth * n_oth + j2) * 3;
+            atomicAdd(dst + 0, -gx); atomicAdd(dst + 1, -gy); atomicAdd(dst + 2, -gz);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k smallest (score, index) per row
+// ------------------------------------------------------------------------------------------
+constexpr int kTopkThreads = 256;
+
+__device__ __forceinline__ unsigned long long score_key(float s, int i) {
+    unsigned u = __float_as_uint(s);
+    u = (s != s) ? 0xffffffffu : ((u & 0x80000000u) ? ~u : (u | 0x80000000u));  // total order, NaN last
+    return ((unsigned long long)u << 32) | (unsigned)i;
+}
+
+__global__ void __launch_bounds__(kTopkThreads) topk_kernel(const float *__restrict__ scores, int cols, int k, int idx_offset,
+                                                            float *__restrict__ out_scores, int *__restrict__ out_idx) {
+    __shared__ unsigned long long red[kTopkThreads / 32];
+    __shared__ unsigned long long chosen;
+    const float *row = scores + (size_t)blockIdx.x * cols;
+    unsigned long long last = 0ull;
+    bool have_last = false;
+    for (int it = 0; it < k; it++) {
+        unsigned long long m = ~0ull;
+        for (int c = threadIdx.x; c < cols; c += kTopkThreads) {
+            const unsigned long long key = score_key(row[c], c);
+            if ((!have_last || key > last) && key < m) m = key;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
+            m = other < m ? other : m;
+        }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < kTopkThreads / 32; i++) m = red[i] < m ? red[i] : m;
+            chosen = m;
+            const int c = (int)(m & 0xffffffffull);
+            out_scores[(size_t)blockIdx.x * k + it] = row[c];
+            out_idx[(size_t)blockIdx.x * k + it] = c + idx_offset;
+        }
+        __syncthreads();
+        last = chosen;
+        have_last = true;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side helpers
+// ------------------------------------------------------------------------------------------
+int check_pairs(int B, int n1, int n2, int rep1, int mod2) {
+    if (B < 0 || n1 < 0 || n2 < 0) return fail_arg(URED_E_SHAPE, "negative size");
+    if (rep1 < 1 || mod2 < 1) return fail_arg(URED_E_SHAPE, "rep1 and mod2 must be >= 1");
+    if ((long long)B * (long long)(n1 > n2 ? n1 : n2) >= (1ll << 40)) return fail_arg(URED_E_SHAPE, "problem too large");
+    return 0;
+}
+inline int count1_of(int B, int rep1) { return (B + rep1 - 1) / rep1; }
+inline int count2_of(int B, int mod2) { return B < mod2 ? B : mod2; }
+
+template <bool SCREEN, int R>
+int launch_nn(const NNParams &p, int B, cudaStream_t st) {
+    constexpr int NARR = SCREEN ? 4 : 3;
+    const size_t smem = (size_t)kStages * NARR * kTile * sizeof(float);
+    const long long grid = (long long)B * (p.qtiles[0] + p.qtiles[1]);
+    if (grid > 0x7fffffffll) return fail_arg(URED_E_SHAPE, "too many work items for one launch");
+    nn_kernel<SCREEN, R><<<(unsigned)grid, kNNThreads, smem, st>>>(p);
+    return check_cuda(cudaGetLastError(), "nn_kernel launch");
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+int ured_abi_version(void) { return URED_ABI_VERSION; }
+const char *ured_last_error_string(void) { return g_err; }
+
+size_t ured_packed_bytes(int count, int n) {
+    if (count <= 0 || n <= 0) return 256;
+    return align_up((size_t)count * 4 * pad32(n) * sizeof(float), 256) + align_up((size_t)count * sizeof(float), 256);
+}
+
+int ured_pack_clouds(const float *xyz, int count, int n, void *packed, void *stream) {
+    if (count < 0 || n < 0) return fail_arg(URED_E_SHAPE, "negative size");
+    if (count == 0 || n == 0) return 0;
+    if (!xyz || !packed) return fail_arg(URED_E_NULL, "ured_pack_clouds: NULL pointer");
+    if ((uintptr_t)packed % 256) return fail_arg(URED_E_WORKSPACE, "packed image must be 256-byte aligned");
+    PackedView v = view_packed(packed, count, n);
+    pack_kernel<<<count, kPackThreads, 0, (cudaStream_t)stream>>>(xyz, n, v.np, (float *)v.soa, (float *)v.wmax);
+    return check_cuda(cudaGetLastError(), "pack_kernel launch");
+}
+
+int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *xyz2, const void *packed2, int n2, int B,
+                   int rep1, int mod2, float *dist1, float *dist2, int *idx1, int *idx2, unsigned flags, void *stream) {
+    int rc = check_pairs(B, n1, n2, rep1, mod2);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0 || (n1 == 0 && n2 == 0)) return 0;
+    if ((n1 && (!dist1 || !idx1)) || (n2 && (!dist2 || !idx2))) return fail_arg(URED_E_NULL, "ured_nn_packed: NULL output");
+    if (n1 == 0 || n2 == 0) {
+        // the reference kernel never writes when the opposing cloud is empty: zeros stay zeros
+        if (n1) { URED_CUDA(cudaMemsetAsync(dist1, 0, (size_t)B * n1 * 4, st), "memset"); URED_CUDA(cudaMemsetAsync(idx1, 0, (size_t)B * n1 * 4, st), "memset"); }
+        if (n2) { URED_CUDA(cudaMemsetAsync(dist2, 0, (size_t)B * n2 * 4, st), "memset"); URED_CUDA(cudaMemsetAsync(idx2, 0, (size_t)B * n2 * 4, st), "memset"); }
+        return 0;
+    }
+    if (!xyz1 || !xyz2 || !packed1 || !packed2) return fail_arg(URED_E_NULL, "ured_nn_packed: NULL input");
+    const int cnt1 = count1_of(B, rep1), cnt2 = count2_of(B, mod2);
+    PackedView v1 = view_packed(packed1, cnt1, n1), v2 = view_packed(packed2, cnt2, n2);
+    NNParams p;
+    p.xyz[0] = xyz1; p.xyz[1] = xyz2;
+    p.soa[0] = v1.soa; p.soa[1] = v2.soa;
+    p.wmax[0] = v1.wmax; p.wmax[1] = v2.wmax;
+    p.dist[0] = dist1; p.dist[1] = dist2;
+    p.idx[0] = idx1; p.idx[1] = idx2;
+    p.n[0] = n1; p.n[1] = n2;
+    p.np[0] = v1.np; p.np[1] = v2.np;
+    p.rep1 = rep1; p.mod2 = mod2;
+    // queries per CTA: 4 per thread when that still leaves every SM several CTAs, else 2
+    const bool exact = (flags & URED_FLAG_EXACT_ONLY) != 0;
+    const long long items4 = (long long)B * ((n1 + 4 * kNNThreads - 1) / (4 * kNNThreads) + (n2 + 4 * kNNThreads - 1) / (4 * kNNThreads));
+    const int R = items4 >= 148 * 8 ? 4 : 2;
+    p.qtiles[0] = (n1 + R * kNNThreads - 1) / (R * kNNThreads);
+    p.qtiles[1] = (n2 + R * kNNThreads - 1) / (R * kNNThreads);
+    if (exact) return R == 4 ? launch_nn<false, 4>(p, B, st) : launch_nn<false, 2>(p, B, st);
+    return R == 4 ? launch_nn<true, 4>(p, B, st) : launch_nn<true, 2>(p, B, st);
+}
+
+size_t ured_chamfer_workspace_bytes(int B, int n1, int n2) {
+    if (B < 0) B = 0;
+    return ured_packed_bytes(B, n1) + ured_packed_bytes(B, n2);
+}
+
+int ured_chamfer_forward(const float *xyz1, const float *xyz2, int B, int n1, int n2, float *dist1, float *dist2, int *idx1,
+                         int *idx2, void *workspace, size_t workspace_bytes, unsigned flags, void *stream) {
+    int rc = check_pairs(B, n1, n2, 1, B > 0 ? B : 1);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    if (n1 > 0 && n2 > 0) {
+        if (!workspace) return fail_arg(URED_E_NULL, "ured_chamfer_forward: NULL workspace");
+        if ((uintptr_t)workspace % 256) return fail_arg(URED_E_WORKSPACE, "workspace must be 256-byte aligned");
+        if (workspace_bytes < ured_chamfer_workspace_bytes(B, n1, n2)) return fail_arg(URED_E_WORKSPACE, "workspace too small");
+        if (!xyz1 || !xyz2) return fail_arg(URED_E_NULL, "ured_chamfer_forward: NULL input");
+    }
+    void *pk1 = workspace;
+    void *pk2 = (char *)workspace + ured_packed_bytes(B, n1);
+    if (n1 > 0 && n2 > 0) {
+        rc = ured_pack_clouds(xyz1, B, n1, pk1, stream);
+        if (rc) return rc;
+        rc = ured_pack_clouds(xyz2, B, n2, pk2, stream);
+        if (rc) return rc;
+    }
+    return ured_nn_packed(xyz1, pk1, n1, xyz2, pk2, n2, B, 1, B, dist1, dist2, idx1, idx2, flags, stream);
+}
+
+int ured_dcd_forward(const float *dist1, const float *dist2, const int *idx1, const int *idx2, int B, int n1, int n2,
+                     float alpha, float n_lambda, float frac_12, float frac_21, float *loss, float *cd_p, float *cd_t,
+                     float *ew1, float *ew2, void *stream) {
+    if (B < 0 || n1 < 0 || n2 < 0) return fail_arg(URED_E_SHAPE, "negative size");
+    if (B == 0) return 0;
+    if (n1 == 0 || n2 == 0) return fail_arg(URED_E_SHAPE, "ured_dcd_forward: empty cloud");
+    if (!dist1 || !dist2 || !idx1 || !idx2) return fail_arg(URED_E_NULL, "ured_dcd_forward: NULL input");
+    const size_t smem = (size_t)(n1 + n2) * sizeof(int);
+    if (smem > 200 * 1024) return fail_arg(URED_E_RANGE, "ured_dcd_forward: n1 + n2 > 51200 points per pair not supported");
+    static thread_local bool attr_done = false;
+    if (!attr_done) {
+        URED_CUDA(cudaFuncSetAttribute(dcd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "dcd smem attribute");
+        attr_done = true;
+    }
+    dcd_fwd_kernel<<<B, kDcdThreads, smem, (cudaStream_t)stream>>>(dist1, dist2, idx1, idx2, n1, n2, alpha, n_lambda, frac_12,
+                                                                   frac_21, loss, cd_p, cd_t, ew1, ew2);
+    return check_cuda(cudaGetLastError(), "dcd_fwd_kernel launch");
+}
+
+int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n2, int rep1, int mod2, const float *dist1,
+                      const float *dist2, const int *idx1, const int *idx2, const float *ew1, const float *ew2, float alpha,
+                      const float *g_loss, const float *g_cd_p, const float *g_cd_t, const float *g_dist1,
+                      const float *g_dist2, float *gradxyz1, float *gradxyz2, void *stream) {
+    int rc = check_pairs(B, n1, n2, rep1, mod2);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cnt1 = count1_of(B, rep1), cnt2 = count2_of(B, mod2);
+    if (B == 0) return 0;
+    if (n1 && !gradxyz1) return fail_arg(URED_E_NULL, "ured_dcd_backward: NULL gradxyz1");
+    if (n2 && !gradxyz2) return fail_arg(URED_E_NULL, "ured_dcd_backward: NULL gradxyz2");
+    const bool shared1 = rep1 != 1, shared2 = mod2 < B;
+    if (n1 == 0 || n2 == 0 || shared1) { if (n1) URED_CUDA(cudaMemsetAsync(gradxyz1, 0, (size_t)cnt1 * n1 * 12, st), "memset"); }
+    if (n1 == 0 || n2 == 0 || shared2) { if (n2) URED_CUDA(cudaMemsetAsync(gradxyz2, 0, (size_t)cnt2 * n2 * 12, st), "memset"); }
+    if (n1 == 0 || n2 == 0) return 0;
+    if (!xyz1 || !xyz2 || !idx1 || !idx2) return fail_arg(URED_E_NULL, "ured_dcd_backward: NULL input");
+    if (g_loss && (!ew1 || !ew2)) return fail_arg(URED_E_NULL, "ured_dcd_backward: g_loss needs ew1/ew2");
+    if (g_cd_p && (!dist1 || !dist2)) return fail_arg(URED_E_NULL, "ured_dcd_backward: g_cd_p needs dist1/dist2");
+    GradParams p;
+    p.xyz[0] = xyz1; p.xyz[1] = xyz2;
+    p.dist[0] = dist1; p.dist[1] = dist2;
+    p.idx[0] = idx1; p.idx[1] = idx2;
+    p.ew[0] = ew1; p.ew[1] = ew2;
+    p.g_dist[0] = g_dist1; p.g_dist[1] = g_dist2;
+    p.g_loss = g_loss; p.g_cd_p = g_cd_p; p.g_cd_t = g_cd_t;
+    p.grad[0] = gradxyz1; p.grad[1] = gradxyz2;
+    p.n[0] = n1; p.n[1] = n2;
+    p.rep1 = rep1; p.mod2 = mod2;
+    p.alpha = alpha;
+    int gx = (n1 + n2 + kGradThreads - 1) / kGradThreads;
+    if (gx > 64) gx = 64;
+    if (B > 65535) return fail_arg(URED_E_SHAPE, "ured_dcd_backward: B > 65535 pairs per call");
+    dim3 grid(gx, B);
+    if (!shared1 && !shared2) grad_kernel<0, false, false><<<grid, kGradThreads, 0, st>>>(p);
+    else if (shared1 && !shared2) grad_kernel<0, true, false><<<grid, kGradThreads, 0, st>>>(p);
+    else if (!shared1 && shared2) grad_kernel<0, false, true><<<grid, kGradThreads, 0, st>>>(p);
+    else grad_kernel<0, true, true><<<grid, kGradThreads, 0, st>>>(p);
+    URED_CUDA(cudaGetLastError(), "grad_kernel<own> launch");
+    grad_kernel<1, false, false><<<grid, kGradThreads, 0, st>>>(p);
+    return check_cuda(cudaGetLastError(), "grad_kernel<scatter> launch");
+}
+
+int ured_chamfer_backward(const float *xyz1, const float *xyz2, int B, int n1, int n2, int rep1, int mod2,
+                          const float *graddist1, const float *graddist2, const int *idx1, const int *idx2, float *gradxyz1,
+                          float *gradxyz2, void *stream) {
+    return ured_dcd_backward(xyz1, xyz2, B, n1, n2, rep1, mod2, nullptr, nullptr, idx1, idx2, nullptr, nullptr, 0.0f, nullptr,
+                             nullptr, nullptr, graddist1, graddist2, gradxyz1, gradxyz2, stream);
+}
+
+int ured_topk_smallest(const float *scores, int rows, int cols, int k, int idx_offset, float *out_scores, int *out_idx,
+                       void *stream) {
+    if (rows < 0 || cols < 0 || k < 0) return fail_arg(URED_E_SHAPE, "negative size");
+    if (k > cols || k > 1024) return fail_arg(URED_E_RANGE, "ured_topk_smallest: need k <= cols and k <= 1024");
+    if (rows == 0 || k == 0) return 0;
+    if (!scores || !out_scores || !out_idx) return fail_arg(URED_E_NULL, "ured_topk_smallest: NULL pointer");
+    topk_kernel<<<rows, kTopkThreads, 0, (cudaStream_t)stream>>>(scores, cols, k, idx_offset, out_scores, out_idx);
+    return check_cuda(cudaGetLastError(), "topk_kernel launch");
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+"""`chamfer_3DDist` -- the reference's Python surface over the B200 kernels.
+
+Mirrors Density_aware_Chamfer_Distance/utils_v2/metrics/CD/chamfer3D/dist_chamfer_3D.py:26-74:
+``chamfer_3DDist()(xyz1, xyz2) -> (dist1, dist2, idx1, idx2)`` with float32 squared
+nearest-neighbour distances and int32 argmin indices on the input device, differentiable in
+both clouds.  Differences, all deliberate:
+  * the native op is the C-ABI library (ctypes), launched on the caller's current stream
+    instead of the legacy default stream (chamfer3D.cu:142-143);
+  * outputs are allocated on the device (the reference builds them on the CPU and copies,
+    dist_chamfer_3D.py:33-42) and a failing native call raises instead of being ignored (:45);
+  * idx1/idx2 are marked non-differentiable.
+GPU tensors only, as in the reference (:25) -- there is no CPU fallback.
+"""
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from . import _native
+
+
+def _require_cloud(name, t):
+    if not isinstance(t, torch.Tensor) or t.dim() != 3 or t.size(-1) != 3:
+        raise ValueError(f"{name} must be a [B, N, 3] tensor, got {tuple(t.shape) if hasattr(t, 'shape') else type(t)}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: GPU tensors only (the B200 Chamfer op has no CPU path)")
+    if t.dtype != torch.float32:
+        # the reference calls .data<float>() on the tensor, which throws for any other dtype
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def nn_forward(xyz1, xyz2, exact_only=False):
+    """Raw forward: (dist1, dist2, idx1, idx2) for contiguous float32 CUDA clouds."""
+    lib = _native.load()
+    B, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    if xyz2.shape[0] != B:
+        raise ValueError(f"batch mismatch: {B} vs {xyz2.shape[0]}")
+    dev = xyz1.device
+    dist1 = torch.empty(B, n, device=dev, dtype=torch.float32)
+    dist2 = torch.empty(B, m, device=dev, dtype=torch.float32)
+    idx1 = torch.empty(B, n, device=dev, dtype=torch.int32)
+    idx2 = torch.empty(B, m, device=dev, dtype=torch.int32)
+    ws_bytes = lib.ured_chamfer_workspace_bytes(B, n, m)
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    flags = _native.URED_FLAG_EXACT_ONLY if exact_only else 0
+    with torch.cuda.device(dev):
+        rc = lib.ured_chamfer_forward(_native.ptr(xyz1), _native.ptr(xyz2), B, n, m,
+                                      _native.ptr(dist1), _native.ptr(dist2), _native.ptr(idx1), _native.ptr(idx2),
+                                      _native.ptr(ws), ws_bytes, flags, _stream(dev))
+    _native.check(rc, "ured_chamfer_forward")
+    return dist1, dist2, idx1, idx2
+
+
+def nn_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2):
+    """Raw backward: (gradxyz1, gradxyz2); either upstream gradient may be None."""
+    lib = _native.load()
+    B, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dev = xyz1.device
+    gradxyz1 = torch.empty_like(xyz1)
+    gradxyz2 = torch.empty_like(xyz2)
+    with torch.cuda.device(dev):
+        rc = lib.ured_chamfer_backward(_native.ptr(xyz1), _native.ptr(xyz2), B, n, m, 1, max(B, 1),
+                                       _native.ptr(graddist1), _native.ptr(graddist2),
+                                       _native.ptr(idx1), _native.ptr(idx2),
+                                       _native.ptr(gradxyz1), _native.ptr(gradxyz2), _stream(dev))
+    _native.check(rc, "ured_chamfer_backward")
+    return gradxyz1, gradxyz2
+
+
+class chamfer_3DFunction(Function):
+    """dist_chamfer_3D.py:26-64."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2):
+        dist1, dist2, idx1, idx2 = nn_forward(xyz1, xyz2)
+        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        ctx.mark_non_differentiable(idx1, idx2)
+        ctx.set_materialize_grads(False)
+        return dist1, dist2, idx1, idx2
+
+    @staticmethod
+    def backward(ctx, graddist1, graddist2, gradidx1, gradidx2):
+        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        if graddist1 is not None:
+            graddist1 = graddist1.contiguous().float()
+        if graddist2 is not None:
+            graddist2 = graddist2.contiguous().float()
+        return nn_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2)
+
+
+class chamfer_3DDist(nn.Module):
+    """dist_chamfer_3D.py:67-74."""
+
+    def __init__(self):
+        super(chamfer_3DDist, self).__init__()
+
+    def forward(self, input1, input2):
+        _require_cloud("input1", input1)
+        _require_cloud("input2", input2)
+        input1 = input1.contiguous()
+        input2 = input2.contiguous()
+        return chamfer_3DFunction.apply(input1, input2)

@@ -1,0 +1,225 @@
+"""Retrieval scoring and ranking on top of the Chamfer/DCD kernels.
+
+Workloads: rank a partial target against K deformed candidates, or
+against a whole source library, by cd_t ("cd_m" in the reference's pickles), cd_p ("cd_s") or
+dcd -- what engine/generate_pair.py:69-122 does one B=1 call at a time through
+engine/geometry_utils.py:80-82, followed by torch.topk(cd_m, k, largest=False)
+(dataset/dataset_utils.py:1043-1051).
+
+Orientation follows compute_dcd_loss(p1, p2) = calc_dcd(x=p1, gt=p2) with x = candidate /
+library shape and gt = target: cloud 1 of the kernel is the target (broadcast over its
+candidates, never copied), cloud 2 the candidate.
+
+Sharded retrieval: the library is split contiguously over ranks (one process per GPU); every
+rank scores its shard, takes a local top-k with global shape ids, and ONE all_gather of
+[Q, k] (score, id) pairs over NCCL/NVLink merges them; all ranks end with the same ranking.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _native
+from .dist_chamfer_3D import _require_cloud, _stream
+
+
+class PackedClouds:
+    """[count, n, 3] float32 CUDA clouds plus their resident packed SoA image (TMA source)."""
+
+    def __init__(self, xyz):
+        if xyz.dim() == 2:
+            xyz = xyz.unsqueeze(0)
+        _require_cloud("xyz", xyz)
+        self.xyz = xyz.contiguous()
+        self.count, self.n, _ = self.xyz.shape
+        lib = _native.load()
+        nbytes = lib.ured_packed_bytes(self.count, self.n)
+        self.packed = torch.empty(nbytes, device=self.xyz.device, dtype=torch.uint8)
+        with torch.cuda.device(self.xyz.device):
+            rc = lib.ured_pack_clouds(_native.ptr(self.xyz), self.count, self.n, _native.ptr(self.packed),
+                                      _stream(self.xyz.device))
+        _native.check(rc, "ured_pack_clouds")
+
+    @property
+    def device(self):
+        return self.xyz.device
+
+
+def _as_packed(c):
+    return c if isinstance(c, PackedClouds) else PackedClouds(c)
+
+
+def nn_pairs(cloud1, cloud2, B, rep1, mod2, first2=0, count2=None, exact_only=False):
+    """Nearest neighbours for B pairs: pair b = (cloud1[b // rep1], cloud2[first2 + b % mod2])."""
+    lib = _native.load()
+    c1, c2 = _as_packed(cloud1), _as_packed(cloud2)
+    count2 = c2.count - first2 if count2 is None else count2
+    if (B + rep1 - 1) // rep1 > c1.count or min(B, mod2) > count2:
+        raise ValueError("pair addressing runs past the clouds provided")
+    dev = c1.device
+    n1, n2 = c1.n, c2.n
+    dist1 = torch.empty(B, n1, device=dev, dtype=torch.float32)
+    dist2 = torch.empty(B, n2, device=dev, dtype=torch.float32)
+    idx1 = torch.empty(B, n1, device=dev, dtype=torch.int32)
+    idx2 = torch.empty(B, n2, device=dev, dtype=torch.int32)
+    # a window [first2, first2+count2) of a packed image: SoA part and max-norm part are offset separately,
+    # so windows are only taken when they start at 0 or the caller packed the shard on its own
+    if first2 != 0:
+        raise ValueError("pack each library shard separately (first2 must be 0)")
+    flags = _native.URED_FLAG_EXACT_ONLY if exact_only else 0
+    with torch.cuda.device(dev):
+        rc = lib.ured_nn_packed(_native.ptr(c1.xyz), _native.ptr(c1.packed), n1,
+                                _native.ptr(c2.xyz), _native.ptr(c2.packed), n2,
+                                B, rep1, mod2,
+                                _native.ptr(dist1), _native.ptr(dist2), _native.ptr(idx1), _native.ptr(idx2),
+                                flags, _stream(dev))
+    _native.check(rc, "ured_nn_packed")
+    return dist1, dist2, idx1, idx2
+
+
+def pair_scores(dist1, dist2, idx1, idx2, alpha=1000, n_lambda=1):
+    """(dcd, cd_p, cd_t), each [B], from raw NN results of chamfer(gt, x) (model_utils.py:31-58)."""
+    lib = _native.load()
+    B, n1 = dist1.shape
+    n2 = dist2.shape[1]
+    dev = dist1.device
+    out = torch.empty(3, B, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        rc = lib.ured_dcd_forward(_native.ptr(dist1), _native.ptr(dist2), _native.ptr(idx1), _native.ptr(idx2),
+                                  B, n1, n2, float(alpha), float(n_lambda), float(n2 / n1), float(n1 / n2),
+                                  _native.ptr(out[0]), _native.ptr(out[1]), _native.ptr(out[2]),
+                                  None, None, _stream(dev))
+    _native.check(rc, "ured_dcd_forward")
+    return out[0], out[1], out[2]
+
+
+def score_candidates(targets, candidates, alpha=1000, n_lambda=1, exact_only=False):
+    """Score Q targets [Q, N, 3] against their K candidates [Q, K, M, 3].
+
+    Returns {"dcd", "cd_p", "cd_t"}: each [Q, K], equal to calc_dcd(candidates[q, k], targets[q]).
+    """
+    if candidates.dim() != 4:
+        raise ValueError("candidates must be [Q, K, M, 3]")
+    Q, K, M, _ = candidates.shape
+    if targets.shape[0] != Q:
+        raise ValueError("one target per candidate set")
+    cands = PackedClouds(candidates.reshape(Q * K, M, 3).float())
+    tgts = _as_packed(targets.float() if not isinstance(targets, PackedClouds) else targets)
+    raw = nn_pairs(tgts, cands, Q * K, K, Q * K, exact_only=exact_only)
+    dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda)
+    return {"dcd": dcd.view(Q, K), "cd_p": cd_p.view(Q, K), "cd_t": cd_t.view(Q, K)}
+
+
+def score_library(targets, library, alpha=1000, n_lambda=1, max_pairs=8192, exact_only=False):
+    """Score every target [Q, N, 3] against every library shape: {"dcd","cd_p","cd_t"} each [Q, S].
+
+    ``library`` is a PackedClouds (packed once, kept resident) or a [S, M, 3] tensor.  Work is cut
+    into slabs of at most ``max_pairs`` (target, shape) pairs so that the per-point NN results
+    (8 bytes per point per pair) stay a bounded scratch buffer instead of Q*S*(N+M)*8 bytes.
+    """
+    tgts = _as_packed(targets.float() if not isinstance(targets, PackedClouds) else targets)
+    lib_c = _as_packed(library)
+    Q, S = tgts.count, lib_c.count
+    out = torch.empty(3, Q, S, device=tgts.device, dtype=torch.float32)
+    if S == 0 or Q == 0:
+        return {"dcd": out[0], "cd_p": out[1], "cd_t": out[2]}
+    q_step = max(1, min(Q, max_pairs // S)) if S <= max_pairs else 1
+    for q0 in range(0, Q, q_step):
+        q1 = min(Q, q0 + q_step)
+        sub_t = tgts if (q0 == 0 and q1 == Q) else PackedClouds(tgts.xyz[q0:q1])
+        if S <= max_pairs:
+            raw = nn_pairs(sub_t, lib_c, (q1 - q0) * S, S, S, exact_only=exact_only)
+            dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda)
+            out[0, q0:q1] = dcd.view(q1 - q0, S)
+            out[1, q0:q1] = cd_p.view(q1 - q0, S)
+            out[2, q0:q1] = cd_t.view(q1 - q0, S)
+        else:  # one target at a time against slabs of the library
+            for s0 in range(0, S, max_pairs):
+                s1 = min(S, s0 + max_pairs)
+                slab = PackedClouds(lib_c.xyz[s0:s1])
+                raw = nn_pairs(sub_t, slab, s1 - s0, s1 - s0, s1 - s0, exact_only=exact_only)
+                dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda)
+                out[0, q0, s0:s1] = dcd
+                out[1, q0, s0:s1] = cd_p
+                out[2, q0, s0:s1] = cd_t
+    return {"dcd": out[0], "cd_p": out[1], "cd_t": out[2]}
+
+
+def topk_smallest(scores, k, idx_offset=0):
+    """k smallest per row in ascending (score, index) order -> (values [rows,k], indices int32 [rows,k]).
+
+    torch.topk(scores, k, largest=False) with the tie order pinned to lowest index first.
+    """
+    if scores.dim() == 1:
+        v, i = topk_smallest(scores.unsqueeze(0), k, idx_offset)
+        return v[0], i[0]
+    if not scores.is_cuda:
+        raise RuntimeError("topk_smallest: GPU tensors only")
+    lib = _native.load()
+    scores = scores.contiguous().float()
+    rows, cols = scores.shape
+    vals = torch.empty(rows, k, device=scores.device, dtype=torch.float32)
+    idx = torch.empty(rows, k, device=scores.device, dtype=torch.int32)
+    with torch.cuda.device(scores.device):
+        rc = lib.ured_topk_smallest(_native.ptr(scores), rows, cols, k, int(idx_offset),
+                                    _native.ptr(vals), _native.ptr(idx), _stream(scores.device))
+    _native.check(rc, "ured_topk_smallest")
+    return vals, idx
+
+
+def retrieve(targets, library, k=10, metric="cd_t", **score_kw):
+    """Top-k library shapes per target: (scores [Q,k], shape ids int32 [Q,k])."""
+    scores = score_library(targets, library, **score_kw)[metric]
+    return topk_smallest(scores, min(k, scores.shape[1]))
+
+
+# ---- sharding over ranks ---------------------------------------------------------------------
+
+def shard_bounds(num_shapes, world_size, rank):
+    """Contiguous shard [lo, hi) of rank `rank`: ceil(S / world) shapes each, the tail may be short or empty."""
+    per = (num_shapes + world_size - 1) // world_size
+    lo = min(num_shapes, rank * per)
+    return lo, min(num_shapes, lo + per)
+
+
+def merge_topk(scores, ids, k):
+    """Merge candidate lists [Q, C] by ascending (score, id); ids < 0 mark padding.  Device-agnostic."""
+    scores = torch.where(ids < 0, torch.full_like(scores, float("inf")), scores)
+    big = torch.iinfo(ids.dtype).max
+    order = torch.sort(torch.where(ids < 0, torch.full_like(ids, big), ids), dim=1, stable=True).indices
+    s = torch.gather(scores, 1, order)
+    i = torch.gather(ids, 1, order)
+    order = torch.sort(s, dim=1, stable=True).indices
+    return torch.gather(s, 1, order)[:, :k], torch.gather(i, 1, order)[:, :k]
+
+
+def gather_and_merge(local_scores, local_ids, k, group=None):
+    """all_gather every rank's local top-k [Q, k_local<=k] (padded to k) and merge; same result on all ranks."""
+    Q = local_scores.shape[0]
+    pad = k - local_scores.shape[1]
+    if pad > 0:
+        local_scores = torch.cat([local_scores, local_scores.new_full((Q, pad), float("inf"))], 1)
+        local_ids = torch.cat([local_ids, local_ids.new_full((Q, pad), -1)], 1)
+    # one message: (score bits, id) as int32 pairs
+    msg = torch.stack([local_scores.contiguous().view(torch.int32), local_ids.to(torch.int32)], dim=-1).contiguous()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        out = torch.empty((world * Q,) + tuple(msg.shape[1:]), dtype=msg.dtype, device=msg.device)
+        dist.all_gather_into_tensor(out, msg, group=group)  # rank-major concatenation along dim 0
+        out = out.view((world,) + tuple(msg.shape))
+    else:
+        out = msg.unsqueeze(0)
+    allmsg = out.permute(1, 0, 2, 3).reshape(Q, -1, 2)
+    return merge_topk(allmsg[..., 0].contiguous().view(torch.float32), allmsg[..., 1].contiguous(), k)
+
+
+def retrieve_sharded(targets, local_library, shard_offset, k=10, metric="cd_t", group=None, **score_kw):
+    """Sharded top-k: `local_library` holds this rank's shapes, whose global ids start at `shard_offset`."""
+    lib_c = _as_packed(local_library) if local_library is not None else None
+    Q = targets.count if isinstance(targets, PackedClouds) else targets.shape[0]
+    dev = targets.device
+    if lib_c is None or lib_c.count == 0:
+        ls = torch.empty(Q, 0, device=dev, dtype=torch.float32)
+        li = torch.empty(Q, 0, device=dev, dtype=torch.int32)
+    else:
+        scores = score_library(targets, lib_c, **score_kw)[metric]
+        ls, li = topk_smallest(scores, min(k, lib_c.count), idx_offset=shard_offset)
+    return gather_and_merge(ls, li, k, group=group)

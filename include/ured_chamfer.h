@@ -1,0 +1,142 @@
+/*
+ * ured_chamfer.h -- C ABI of the B200-native Chamfer / density-aware Chamfer (DCD) hot path.
+ *
+ * This is the drop-in boundary for ONE path of the U-RED reference: the native Chamfer op
+ * (pybind module `chamfer_3D`) and the torch-op body of `calc_dcd` / `calc_cd` built on it.
+ * Paths below are relative to the reference tree; DCD/ = Density_aware_Chamfer_Distance/.
+ *
+ *   reference interface                                              replaced by
+ *   ---------------------------------------------------------------  ---------------------------
+ *   chamfer_3D.forward(xyz1,xyz2,dist1,dist2,idx1,idx2)              ured_chamfer_forward
+ *       DCD/utils_v2/metrics/CD/chamfer3D/chamfer_cuda.cpp:17-19,31
+ *       -> chamfer_cuda_forward            .../chamfer3D.cu:136-154
+ *       -> NmDistanceKernel x2             .../chamfer3D.cu:12-134
+ *   chamfer_3D.backward(xyz1,xyz2,gradxyz1,gradxyz2,graddist1,       ured_chamfer_backward
+ *                       graddist2,idx1,idx2)
+ *       .../chamfer_cuda.cpp:22-26,32 -> chamfer3D.cu:155-195
+ *   torch-op body of calc_cd / calc_dcd                              ured_dcd_forward,
+ *       DCD/utils_v2/model_utils.py:13-51, 53-70                     ured_dcd_backward
+ *   torch.topk(cd_m, k, largest=False) ranking                       ured_topk_smallest
+ *       dataset/dataset_utils.py:1043-1051
+ *
+ * Conventions (all entry points)
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *     (the library never allocates or frees device memory and keeps no global state);
+ *   - clouds are row-major contiguous float32 [count, n, 3]; distances float32; indices int32
+ *     (same dtypes as the reference: dist_chamfer_3D.py:33-37);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it
+ *     and no entry point synchronises the device;
+ *   - return value: 0 on success, a positive cudaError_t value on a CUDA failure, a negative
+ *     URED_E_* value on an argument error.  ured_last_error_string() describes the last
+ *     failure seen by the calling thread.  (The reference printf()s and returns 0/1, and its
+ *     Python wrapper ignores the result: chamfer3D.cu:145-151, dist_chamfer_3D.py:45.)
+ *   - re-entrant: concurrent calls from several host threads / streams are allowed as long as
+ *     they do not share output or workspace buffers.
+ *
+ * Pair addressing.  A call evaluates B ordered cloud pairs.  Pair b uses cloud-1 entry
+ * (b / rep1) and cloud-2 entry (b % mod2); count1 = ceil(B / rep1) and count2 = min(B, mod2)
+ * clouds must be present.  rep1 = 1, mod2 = B is the reference's plain batched call;
+ * rep1 = K scores one target against its K candidates; rep1 = S, mod2 = S scores every target
+ * against every one of S library shapes.
+ */
+#ifndef URED_CHAMFER_H_
+#define URED_CHAMFER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define URED_ABI_VERSION 1
+
+/* argument errors (negative so that they never collide with cudaError_t) */
+#define URED_E_NULL      (-1) /* a required pointer is NULL */
+#define URED_E_SHAPE     (-2) /* negative size, or rep1/mod2 out of range */
+#define URED_E_WORKSPACE (-3) /* workspace too small or misaligned (needs 256-byte alignment) */
+#define URED_E_RANGE     (-4) /* k, n_lambda, ... out of the supported range */
+
+/* flags for the forward entry points */
+#define URED_FLAG_EXACT_ONLY 1u /* skip the 3-FFMA screening pass; run the difference-form kernel on every pair */
+
+int ured_abi_version(void);
+const char *ured_last_error_string(void);
+
+/* ---- packed clouds ---------------------------------------------------------------------
+ * The nearest-neighbour kernel stages the opposing cloud through shared memory with TMA bulk
+ * copies from a packed, padded structure-of-arrays image: per cloud X[np] | Y[np] | Z[np] |
+ * W[np] with np = n rounded up to 32, W = x^2+y^2+z^2, padding = copies of the last point;
+ * followed (at the end of the whole image) by one float per cloud holding max W.
+ * A library that is scored against many targets is packed once and kept resident. */
+size_t ured_packed_bytes(int count, int n);
+int ured_pack_clouds(const float *xyz, int count, int n, void *packed, void *stream);
+
+/* ---- nearest neighbours on packed clouds (both directions, one launch) --------------------
+ * dist1/idx1: [B, n1]  for every point of cloud 1, squared distance to / index of its nearest
+ *                      point in cloud 2 (lowest index on ties);  dist2/idx2: [B, n2] vice versa.
+ * Results are bit-identical to NmDistanceKernel (chamfer3D.cu:12-134) for finite inputs. */
+int ured_nn_packed(const float *xyz1, const void *packed1, int n1,
+                   const float *xyz2, const void *packed2, int n2,
+                   int B, int rep1, int mod2,
+                   float *dist1, float *dist2, int *idx1, int *idx2,
+                   unsigned flags, void *stream);
+
+/* ---- drop-in for chamfer_3D.forward ---------------------------------------------------------
+ * workspace: ured_chamfer_workspace_bytes(B, n1, n2) bytes, 256-byte aligned. */
+size_t ured_chamfer_workspace_bytes(int B, int n1, int n2);
+int ured_chamfer_forward(const float *xyz1, const float *xyz2, int B, int n1, int n2,
+                         float *dist1, float *dist2, int *idx1, int *idx2,
+                         void *workspace, size_t workspace_bytes,
+                         unsigned flags, void *stream);
+
+/* ---- drop-in for chamfer_3D.backward ---------------------------------------------------------
+ * gradxyz1 [count1, n1, 3] and gradxyz2 [count2, n2, 3] are OVERWRITTEN (the reference
+ * accumulates into caller-zeroed buffers; here the zero-fill is part of the call).
+ * graddist1 / graddist2 may be NULL (treated as zeros). */
+int ured_chamfer_backward(const float *xyz1, const float *xyz2, int B, int n1, int n2,
+                          int rep1, int mod2,
+                          const float *graddist1, const float *graddist2,
+                          const int *idx1, const int *idx2,
+                          float *gradxyz1, float *gradxyz2, void *stream);
+
+/* ---- calc_cd / calc_dcd epilogue ------------------------------------------------------------
+ * From (dist1, idx1) [B, n1] and (dist2, idx2) [B, n2] of chamfer(gt, x) -- note the
+ * reference's argument swap, model_utils.py:56: cloud 1 = gt, cloud 2 = x -- computes per pair
+ *   cd_p = (mean sqrt(dist1) + mean sqrt(dist2)) / 2                     model_utils.py:57
+ *   cd_t =  mean dist1 + mean dist2                                      model_utils.py:58
+ *   loss = (mean_i(1 - exp(-alpha d1_i) w1_i) + mean_j(1 - exp(-alpha d2_j) w2_j)) / 2
+ *          w1_i = frac_21 / (count1[idx1_i]^n_lambda + 1e-6), count1 = histogram of idx1
+ *          over the n2 points of cloud 2; symmetric for w2 with frac_12     model_utils.py:31-45
+ * ew1 [B, n1] / ew2 [B, n2] (optional, may be NULL) receive exp(-alpha d) * w per point, the
+ * only per-point state the backward pass needs.  Sums are accumulated in float64. */
+int ured_dcd_forward(const float *dist1, const float *dist2, const int *idx1, const int *idx2,
+                     int B, int n1, int n2,
+                     float alpha, float n_lambda, float frac_12, float frac_21,
+                     float *loss, float *cd_p, float *cd_t,
+                     float *ew1, float *ew2, void *stream);
+
+/* Fused backward of [loss, cd_p, cd_t, dist1, dist2] w.r.t. both clouds: builds the per-point
+ * d(out)/d(dist) coefficient and applies the Chamfer backward (chamfer3D.cu:155-174) in the
+ * same pass.  Any of g_loss/g_cd_p/g_cd_t [B] and g_dist1 [B,n1] / g_dist2 [B,n2] may be NULL.
+ * ew1/ew2 are required when g_loss is given.  gradxyz1/gradxyz2 are overwritten. */
+int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n2,
+                      int rep1, int mod2,
+                      const float *dist1, const float *dist2, const int *idx1, const int *idx2,
+                      const float *ew1, const float *ew2, float alpha,
+                      const float *g_loss, const float *g_cd_p, const float *g_cd_t,
+                      const float *g_dist1, const float *g_dist2,
+                      float *gradxyz1, float *gradxyz2, void *stream);
+
+/* ---- ranking ----------------------------------------------------------------------------------
+ * For each of `rows` score rows of length `cols`: the k smallest entries in ascending
+ * (score, index) order -- torch.topk(..., largest=False) with its unspecified tie order pinned
+ * to "lowest index first"; NaN sorts last.  out_idx gets index + idx_offset (global shape ids
+ * of a library shard).  k <= cols is required; k <= 1024. */
+int ured_topk_smallest(const float *scores, int rows, int cols, int k, int idx_offset,
+                       float *out_scores, int *out_idx, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* URED_CHAMFER_H_ */

@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library loads, exports every symbol include/*.h declares, and validates arguments
+before touching the device (no compute calls here -- there is no GPU in this suite)."""
+import ctypes
+import glob
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        names |= set(re.findall(r"\b(ured_\w+)\s*\(", text))
+    return sorted(names)
+
+
+def test_header_symbols_are_exported(ured):
+    lib = ctypes.CDLL(ured._native.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 11
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ but not exported"
+    assert set(syms) == set(ured._native.EXPORTED_SYMBOLS), "ctypes binding and header disagree"
+
+
+def test_abi_version_and_sizes(ured):
+    lib = ured._native.load()
+    assert lib.ured_abi_version() == 1
+    # 2 clouds of 2048 points: 2 * 4 arrays * 2048 floats, plus one max-norm float per cloud, 256-aligned
+    assert lib.ured_packed_bytes(2, 2048) == 2 * 4 * 2048 * 4 + 256
+    assert lib.ured_packed_bytes(1, 100) == 4 * 128 * 4 + 256  # padded to 32 points
+    assert lib.ured_chamfer_workspace_bytes(3, 100, 200) == lib.ured_packed_bytes(3, 100) + lib.ured_packed_bytes(3, 200)
+
+
+def test_argument_errors_do_not_need_a_device(ured):
+    lib = ured._native.load()
+    E_NULL, E_SHAPE, E_RANGE = -1, -2, -4
+    assert lib.ured_chamfer_forward(None, None, 2, 8, 8, None, None, None, None, None, 0, 0, None) == E_NULL
+    assert b"NULL" in lib.ured_last_error_string()
+    assert lib.ured_chamfer_forward(None, None, -1, 8, 8, None, None, None, None, None, 0, 0, None) == E_SHAPE
+    assert lib.ured_nn_packed(None, None, 8, None, None, 8, 4, 0, 4, None, None, None, None, 0, None) == E_SHAPE
+    assert lib.ured_topk_smallest(None, 1, 5, 6, 0, None, None, None) == E_RANGE
+    assert lib.ured_dcd_forward(None, None, None, None, 1, 8, 8, 1.0, 1.0, 1.0, 1.0, None, None, None, None, None, None) == E_NULL
+    # empty batches are a successful no-op
+    assert lib.ured_chamfer_forward(None, None, 0, 8, 8, None, None, None, None, None, 0, 0, None) == 0
+    assert lib.ured_topk_smallest(None, 0, 5, 2, 0, None, None, None) == 0
+
+
+def test_no_cpu_fallback(ured):
+    import torch
+    x = torch.rand(1, 8, 3)
+    with pytest.raises(RuntimeError, match="GPU tensors only"):
+        ured.chamfer_3DDist()(x, x)
+    with pytest.raises(RuntimeError, match="GPU tensors only"):
+        ured.calc_dcd(x, x)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: no file of the shipped package may mention it."""
+    pkg_dir = os.path.join(ROOT, "387-u-red-unsupervised-3d-shape-retrieval-and-deformation-for-partial-point-clouds_b200")
+    for path in glob.glob(os.path.join(pkg_dir, "**", "*"), recursive=True):
+        if path.endswith((".py", ".cu", ".h", ".cpp")):
+            text = open(path).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
+            assert "liboracle" not in text, path

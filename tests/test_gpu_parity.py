@@ -1,0 +1,289 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the oracle.
+
+Bars (BASELINE.json north_star): idx1/idx2 and rankings bit-exact; distances bit-exact (they are
+the same float32 difference-form values); gradients and DCD values within 1e-5 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_clouds
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-5  # north_star tolerance for floating-point outputs
+
+
+def dev(t):
+    return t.cuda()
+
+
+def run_fwd(ured, a, b, exact_only):
+    out = ured.nn_forward(dev(a).contiguous(), dev(b).contiguous(), exact_only=exact_only)
+    torch.cuda.synchronize()
+    return [o.cpu().numpy() for o in out]
+
+
+def assert_bit_exact(got, want, tag=""):
+    for g, w, name in zip(got, want, ["dist1", "dist2", "idx1", "idx2"]):
+        if g.dtype == np.float32:
+            assert np.array_equal(g.view(np.uint32), w.view(np.uint32)), f"{tag} {name} differs: max abs {np.abs(g - w).max()}"
+        else:
+            assert np.array_equal(g, w), f"{tag} {name}: {np.sum(g != w)} indices differ"
+
+
+SHAPES = [  # (B, N, M, kind)
+    (4, 100, 200, "U"),     # the reference unit test, unit_test.py:15-16
+    (2, 2000, 1000, "U"),   # the reference timing shapes, unit_test.py:39-40
+    (1, 1, 1, "U"), (1, 1, 37, "U"), (3, 37, 1, "U"),
+    (2, 31, 33, "U"), (2, 513, 1025, "S"), (1, 1024, 1023, "S"),
+    (5, 2048, 2048, "S"),   # chair
+    (1, 5000, 3000, "U"),   # several 1024-candidate TMA tiles, ragged tail
+    (2, 1024, 2048, "S"),   # per-part loss shape, loss/chamfer_loss.py:23
+]
+
+
+@pytest.mark.parametrize("exact_only", [False, True], ids=["screen", "exact"])
+@pytest.mark.parametrize("B,N,M,kind", SHAPES)
+def test_forward_bit_exact_vs_oracle(ured, oracle, B, N, M, kind, exact_only):
+    a, b = make_clouds(0, B, N, kind), make_clouds(1, B, M, kind)
+    want = oracle.c.chamfer_forward(a.numpy(), b.numpy())
+    assert_bit_exact(run_fwd(ured, a, b, exact_only), want, f"{B}x{N}x{M}")
+
+
+@pytest.mark.parametrize("exact_only", [False, True], ids=["screen", "exact"])
+def test_forward_adversarial_ties_and_duplicates(ured, oracle, exact_only):
+    g = torch.Generator().manual_seed(7)
+    lattice_a = torch.randint(0, 4, (2, 700, 3), generator=g).float()          # masses of exact ties
+    lattice_b = torch.randint(0, 4, (2, 900, 3), generator=g).float()
+    assert_bit_exact(run_fwd(ured, lattice_a, lattice_b, exact_only), oracle.c.chamfer_forward(lattice_a.numpy(), lattice_b.numpy()), "lattice")
+    x = make_clouds(3, 2, 600, "S")
+    dup = torch.cat([x, x[:, :300]], 1)                                          # duplicated candidates
+    assert_bit_exact(run_fwd(ured, x, dup, exact_only), oracle.c.chamfer_forward(x.numpy(), dup.numpy()), "dup")
+    same = make_clouds(4, 1, 1500, "U")
+    got = run_fwd(ured, same, same, exact_only)                                  # identical clouds: d = 0, idx = self
+    assert_bit_exact(got, oracle.c.chamfer_forward(same.numpy(), same.numpy()), "self")
+    assert (got[0] == 0).all() and np.array_equal(got[2][0], np.arange(1500))
+    far = make_clouds(5, 1, 800, "S") + 1000.0                                   # large offset: screening bound must widen
+    far_b = make_clouds(6, 1, 800, "S") + 1000.0
+    assert_bit_exact(run_fwd(ured, far, far_b, exact_only), oracle.c.chamfer_forward(far.numpy(), far_b.numpy()), "offset")
+    tiny = make_clouds(8, 1, 500, "S") * 1e-20                                   # products underflow to denormals / zero
+    tiny_b = make_clouds(9, 1, 400, "S") * 1e-20
+    assert_bit_exact(run_fwd(ured, tiny, tiny_b, exact_only), oracle.c.chamfer_forward(tiny.numpy(), tiny_b.numpy()), "tiny")
+    huge = make_clouds(10, 1, 300, "S") * 1e19                                   # squared distances overflow to +inf
+    huge_b = make_clouds(11, 1, 300, "S") * 1e19
+    assert_bit_exact(run_fwd(ured, huge, huge_b, exact_only), oracle.c.chamfer_forward(huge.numpy(), huge_b.numpy()), "huge")
+
+
+def test_screen_and_exact_kernels_agree_at_full_size(ured):
+    """cfg1-sized (B=32, 2048^2) and a dense 16384^2 pair: the two kernels must give identical bits."""
+    for (B, N, M, kind) in [(32, 2048, 2048, "S"), (1, 16384, 16384, "S"), (1, 16384, 16384, "U")]:
+        a, b = make_clouds(20, B, N, kind), make_clouds(21, B, M, kind)
+        assert_bit_exact(run_fwd(ured, a, b, False), run_fwd(ured, a, b, True), f"full {B}x{N}x{M}")
+
+
+def test_golden_reference_python(ured):
+    """Against the committed outputs of the reference's python Chamfer: its own unit-test criterion."""
+    g = np.load(os.path.join(GOLD, "chamfer_ref_python.npz"))
+    for case in ["unit_test", "timing", "shape", "chair"]:
+        d1, d2, i1, i2 = run_fwd(ured, torch.from_numpy(g[f"{case}_xyz1"]), torch.from_numpy(g[f"{case}_xyz2"]), False)
+        assert np.mean((d1 - g[f"{case}_dist1"]) ** 2) + np.mean((d2 - g[f"{case}_dist2"]) ** 2) < 1e-8
+        assert np.array_equal(i1, g[f"{case}_idx1"]) and np.array_equal(i2, g[f"{case}_idx2"])
+
+
+def rel_err(got, want):
+    scale = np.abs(want).max() + 1e-30
+    return np.abs(got - want).max() / scale
+
+
+@pytest.mark.parametrize("B,N,M", [(4, 100, 200), (2, 2000, 1000), (3, 2048, 2048), (1, 1, 5)])
+def test_backward_vs_oracle(ured, oracle, B, N, M):
+    kind = "S" if min(N, M) > 1 else "U"
+    a, b = make_clouds(0, B, N, kind), make_clouds(1, B, M, kind)
+    g = torch.Generator().manual_seed(2)
+    w1, w2 = torch.randn(B, N, generator=g), torch.randn(B, M, generator=g)
+    xa, xb = dev(a).requires_grad_(), dev(b).requires_grad_()
+    d1, d2, i1, i2 = ured.chamfer_3DDist()(xa, xb)
+    assert i1.dtype == torch.int32 and d1.dtype == torch.float32 and not i1.requires_grad
+    ((d1 * dev(w1)).sum() + (d2 * dev(w2)).sum()).backward()
+    o = oracle.c.chamfer_forward(a.numpy(), b.numpy())
+    r1, r2 = oracle.c.chamfer_backward_f64(a.numpy(), b.numpy(), w1.numpy(), w2.numpy(), o[2], o[3])
+    assert rel_err(xa.grad.cpu().numpy(), r1) < RTOL
+    assert rel_err(xb.grad.cpu().numpy(), r2) < RTOL
+    # only one output used: the other upstream gradient is None
+    xa.grad = None; xb.grad = None
+    d1, d2, _, _ = ured.chamfer_3DDist()(xa, xb)
+    d1.sum().backward()
+    r1, r2 = oracle.c.chamfer_backward_f64(a.numpy(), b.numpy(), np.ones((B, N), np.float32), np.zeros((B, M), np.float32), o[2], o[3])
+    assert rel_err(xa.grad.cpu().numpy(), r1) < RTOL and rel_err(xb.grad.cpu().numpy(), r2) < RTOL
+
+
+DCD_CASES = [(1000, 1, False, 3, 512, 512), (200, 0.5, False, 2, 700, 1024), (40, 0.5, True, 2, 1024, 300),
+             (50, 2, False, 2, 256, 384), (30, 0.7, False, 1, 300, 300), (1000, 1, False, 2, 2048, 2048)]
+
+
+@pytest.mark.parametrize("alpha,lam,non_reg,B,n_x,n_gt", DCD_CASES)
+def test_calc_dcd_value_and_grad_vs_oracle(ured, oracle, alpha, lam, non_reg, B, n_x, n_gt):
+    x0 = make_clouds(40, B, n_x, "S")
+    gt0 = make_clouds(41, B, n_gt, "S") * 0.9 + 0.02 * torch.randn(B, n_gt, 3, generator=torch.Generator().manual_seed(9))
+    w = torch.linspace(0.5, 1.5, B)
+    x, gt = dev(x0).requires_grad_(), dev(gt0).requires_grad_()
+    res = ured.calc_dcd(x, gt, alpha=alpha, n_lambda=lam, return_raw=True, non_reg=non_reg)
+    loss, cd_p, cd_t, dist1, dist2, idx1, idx2 = res
+    xo, gto = x0.clone().requires_grad_(), gt0.clone().requires_grad_()
+    ol, op, ot, od1, od2, oi1, oi2 = oracle.t.calc_dcd_oracle(xo, gto, alpha=alpha, n_lambda=lam, return_raw=True, non_reg=non_reg)
+    assert np.array_equal(idx1.cpu().numpy(), oi1.numpy()) and np.array_equal(idx2.cpu().numpy(), oi2.numpy())
+    assert np.array_equal(dist1.detach().cpu().numpy(), od1.detach().numpy())
+    for got, want, name in [(loss, ol, "loss"), (cd_p, op, "cd_p"), (cd_t, ot, "cd_t")]:
+        assert got.shape == (B,) and got.dtype == torch.float32
+        assert np.allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=RTOL, atol=0), name
+    (loss * dev(w)).sum().backward()
+    (ol * w).sum().backward()
+    assert rel_err(x.grad.cpu().numpy(), xo.grad.numpy()) < RTOL
+    assert rel_err(gt.grad.cpu().numpy(), gto.grad.numpy()) < RTOL
+    # all three outputs in one loss (cd_p's sqrt has finite gradient here: no zero distances)
+    x.grad = None; gt.grad = None; xo.grad = None; gto.grad = None
+    l2, p2, t2 = ured.calc_dcd(x, gt, alpha=alpha, n_lambda=lam, non_reg=non_reg)
+    ((l2 + 0.3 * p2 + 2.0 * t2) * dev(w)).sum().backward()
+    l3, p3, t3 = oracle.t.calc_dcd_oracle(xo, gto, alpha=alpha, n_lambda=lam, non_reg=non_reg)
+    ((l3 + 0.3 * p3 + 2.0 * t3) * w).sum().backward()
+    assert rel_err(x.grad.cpu().numpy(), xo.grad.numpy()) < RTOL
+    assert rel_err(gt.grad.cpu().numpy(), gto.grad.numpy()) < RTOL
+
+
+def test_golden_reference_model_utils(ured):
+    """Against outputs of the reference's UNMODIFIED calc_dcd/calc_cd (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(GOLD, "dcd_ref_model_utils.npz"))
+    for case in ["default", "pcn", "vrc_nonreg", "lambda2"]:
+        alpha, lam, non_reg = g[f"{case}_meta"]
+        lam = int(lam) if float(lam).is_integer() else float(lam)
+        x = dev(torch.from_numpy(g[f"{case}_x"])).requires_grad_()
+        gt = dev(torch.from_numpy(g[f"{case}_gt"])).requires_grad_()
+        w = dev(torch.from_numpy(g[f"{case}_w"]))
+        loss, cd_p, cd_t, dist1, dist2, idx1, idx2 = ured.calc_dcd(x, gt, alpha=alpha, n_lambda=lam, return_raw=True, non_reg=bool(non_reg))
+        assert np.array_equal(idx1.cpu().numpy(), g[f"{case}_idx1"]) and np.array_equal(idx2.cpu().numpy(), g[f"{case}_idx2"])
+        assert np.array_equal(dist1.detach().cpu().numpy(), g[f"{case}_dist1"]) and np.array_equal(dist2.detach().cpu().numpy(), g[f"{case}_dist2"])
+        for got, name in [(loss, "loss"), (cd_p, "cd_p"), (cd_t, "cd_t")]:
+            assert np.allclose(got.detach().cpu().numpy(), g[f"{case}_{name}"], rtol=RTOL, atol=0), (case, name)
+        (loss * w).sum().backward()
+        assert rel_err(x.grad.cpu().numpy(), g[f"{case}_g_x_loss"]) < RTOL
+        assert rel_err(gt.grad.cpu().numpy(), g[f"{case}_g_gt_loss"]) < RTOL
+        x.grad = None; gt.grad = None
+        cd_p2, cd_t2, f1 = ured.calc_cd(x, gt, calc_f1=True)
+        ((cd_p2 + 3 * cd_t2) * w).sum().backward()
+        assert np.allclose(f1.cpu().numpy(), g[f"{case}_f1"], rtol=1e-6)
+        assert rel_err(x.grad.cpu().numpy(), g[f"{case}_g_x_cd"]) < RTOL
+        assert rel_err(gt.grad.cpu().numpy(), g[f"{case}_g_gt_cd"]) < RTOL
+
+
+def test_calc_cd_variants(ured, oracle):
+    x0, gt0 = make_clouds(50, 2, 300, "S"), make_clouds(51, 2, 400, "S")
+    x, gt = dev(x0), dev(gt0)
+    cd_p, cd_t = ured.calc_cd(x, gt)
+    op, ot = oracle.t.calc_cd_oracle(x0, gt0)
+    assert np.allclose(cd_p.cpu().numpy(), op.numpy(), rtol=RTOL) and np.allclose(cd_t.cpu().numpy(), ot.numpy(), rtol=RTOL)
+    sep_p, sep_t = ured.calc_cd(x, gt, separate=True)
+    assert sep_p.shape == (2, 2) and np.allclose((sep_t[0] + sep_t[1]).cpu().numpy(), ot.numpy(), rtol=RTOL)
+    raw = ured.calc_cd(x, gt, return_raw=True)
+    assert len(raw) == 6 and raw[4].dtype == torch.int32
+    # strided inputs are made contiguous like the reference does (dist_chamfer_3D.py:72-73)
+    xs = dev(torch.cat([x0, x0], 2))[:, :, :3]
+    d = ured.chamfer_3DDist()(xs, gt)
+    e = ured.chamfer_3DDist()(x, gt)
+    assert torch.equal(d[0], e[0]) and torch.equal(d[2], e[2])
+    with pytest.raises(TypeError):
+        ured.chamfer_3DDist()(x.double(), gt)
+
+
+def test_chamfer_loss_adaptor(ured, oracle):
+    src0 = make_clouds(60, 2, 3 * 1024, "S")
+    tgt0 = make_clouds(61, 2, 2048, "S")
+    parts0 = [[make_clouds(62 + i, 1, 100 + 37 * i, "S")[0] for i in range(3)], [make_clouds(70 + i, 1, 64 + 11 * i, "S")[0] for i in range(2)]]
+    mask = torch.tensor([[1, 1, 1], [1, 1, 0]])
+    src = dev(src0).requires_grad_()
+    full, part = ured.compute_cm_loss(src, dev(tgt0), [[dev(p) for p in ps] for ps in parts0], dev(mask))
+
+    def cd2(p1, p2):
+        d1, d2, _, _ = oracle.t.oracle_cd(p1, p2)
+        return d1.mean(1) + d2.mean(1)
+    want_full = torch.stack([cd2(src0[b:b + 1, :int(mask[b].sum()) * 1024], tgt0[b:b + 1]) for b in range(2)]).mean()
+    want_part = torch.stack([torch.stack([cd2(src0[b:b + 1, i * 1024:(i + 1) * 1024], parts0[b][i][None]) for i in range(len(parts0[b]))]).mean() for b in range(2)]).mean()
+    assert np.isclose(full.item(), want_full.item(), rtol=RTOL) and np.isclose(part.item(), want_part.item(), rtol=RTOL)
+    (full + part).backward()
+    assert torch.isfinite(src.grad).all() and src.grad.abs().sum() > 0
+    assert torch.allclose(ured.chamfer_distance2(dev(src0[:, :2048]), dev(tgt0)).cpu(), cd2(src0[:, :2048], tgt0), rtol=RTOL)
+
+
+def test_retrieval_scores_and_rankings(ured, oracle):
+    Q, K, N, M = 3, 10, 600, 512
+    tg = make_clouds(80, Q, N, "S")
+    cands = torch.stack([make_clouds(81 + q, K, M, "S") * (0.8 + 0.05 * q) for q in range(Q)])
+    sc = ured.score_candidates(dev(tg), dev(cands), alpha=1000, n_lambda=1)
+    want = {"dcd": [], "cd_p": [], "cd_t": []}
+    for q in range(Q):
+        l, p, t = oracle.t.calc_dcd_oracle(cands[q], tg[q:q + 1].expand(K, N, 3))
+        want["dcd"].append(l); want["cd_p"].append(p); want["cd_t"].append(t)
+    for key in want:
+        w = torch.stack(want[key])
+        assert np.allclose(sc[key].cpu().numpy(), w.numpy(), rtol=RTOL), key
+        # rankings: full ascending order identical to the oracle's (score, index) order
+        got_v, got_i = ured.topk_smallest(sc[key], K)
+        _, want_i = oracle.t.topk_oracle(w, K)
+        assert np.array_equal(got_i.cpu().numpy(), want_i.numpy()), key
+    # library scoring == candidate scoring with a shared library, in one slab and in several
+    libr = make_clouds(90, 37, M, "S")
+    full = ured.score_library(dev(tg), dev(libr))
+    slabs = ured.score_library(dev(tg), ured.PackedClouds(dev(libr)), max_pairs=16)
+    ref = ured.score_candidates(dev(tg), dev(libr.unsqueeze(0).expand(Q, 37, M, 3).contiguous()))
+    for key in full:
+        assert torch.equal(full[key], ref[key]) and torch.equal(slabs[key], ref[key]), key
+    v, i = ured.retrieve(dev(tg), dev(libr), k=10)
+    _, oi = oracle.t.topk_oracle(ref["cd_t"].cpu(), 10)
+    assert np.array_equal(i.cpu().numpy(), oi.numpy())
+
+
+def test_topk_ties_nan_and_offset(ured, oracle):
+    s = torch.tensor([[3.0, 1.0, 1.0, float("nan"), -2.0, 1.0, 0.0, float("inf")],
+                      [0.0, -0.0, 5.0, 5.0, 5.0, -1.0, 2.0, 2.0]])
+    v, i = ured.topk_smallest(dev(s), 6, idx_offset=100)
+    assert i.cpu().tolist() == [[104, 106, 101, 102, 105, 100], [105, 101, 100, 106, 107, 102]]
+    big = torch.rand(4, 20000, generator=torch.Generator().manual_seed(1)).round(decimals=3)  # many ties
+    v, i = ured.topk_smallest(dev(big), 10)
+    ov, oi = oracle.t.topk_oracle(big, 10)
+    assert np.array_equal(i.cpu().numpy(), oi.numpy()) and np.array_equal(v.cpu().numpy(), ov.numpy())
+
+
+def test_sharded_retrieval_matches_single_gpu(ured):
+    """Emulate 4 ranks on one GPU: shard, local top-k with global ids, merge -- same ranking as unsharded."""
+    S, M, Q, k = 50, 256, 3, 10
+    libr = dev(make_clouds(95, S, M, "S"))
+    tg = dev(make_clouds(96, Q, 300, "S"))
+    v, i = ured.retrieve(tg, libr, k=k)
+    loc_s, loc_i = [], []
+    for r in range(4):
+        lo, hi = ured.shard_bounds(S, 4, r)
+        sc = ured.score_library(tg, libr[lo:hi])["cd_t"]
+        a, b = ured.topk_smallest(sc, min(k, hi - lo), idx_offset=lo)
+        loc_s.append(a); loc_i.append(b)
+    ms, mi = ured.merge_topk(torch.cat(loc_s, 1), torch.cat(loc_i, 1), k)
+    assert torch.equal(mi, i) and torch.equal(ms, v)
+    ms, mi = ured.retrieve_sharded(tg, libr, 0, k=k)  # world size 1 path
+    assert torch.equal(mi, i)
+
+
+def test_stream_and_error_behaviour(ured):
+    a, b = dev(make_clouds(0, 2, 400, "S")), dev(make_clouds(1, 2, 300, "S"))
+    want = ured.chamfer_3DDist()(a, b)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        got = ured.chamfer_3DDist()(a, b)
+    s.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(got, want))
+    with pytest.raises(ValueError):
+        ured.chamfer_3DDist()(a, b[:1])
+    empty = ured.chamfer_3DDist()(a[:0], b[:0])
+    assert empty[0].shape == (0, 400)
+    z = ured.chamfer_3DDist()(a, b[:, :0])  # empty opposing cloud: the reference leaves its zero-filled outputs
+    assert (z[0] == 0).all() and (z[2] == 0).all() and z[1].shape == (2, 0)
