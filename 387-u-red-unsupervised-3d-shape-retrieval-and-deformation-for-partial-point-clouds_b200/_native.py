@@ -28,6 +28,7 @@ _SIGNATURES = {
     # name: (restype, argtypes)
     "ured_abi_version": (ctypes.c_int, []),
     "ured_last_error_string": (ctypes.c_char_p, []),
+    "ured_kernel_launches": (ctypes.c_ulonglong, []),
     "ured_packed_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "ured_pack_clouds": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "ured_nn_packed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,

@@ -18,7 +18,7 @@
 //                   EXACT   difference form d = fma(dz,dz,fma(dx,dx,dy*dy)) on every pair
 //                           (the reference arithmetic, 6 FP32-pipe ops per pair);
 //                   SCREEN  3-FFMA expansion form s = |c|^2 - 2 q.c as a filter, then the exact
-//                           difference form only on the winning 16-candidate chunk; queries whose
+//                           difference form only on the winning 32-candidate chunk; queries whose
 //                           runner-up chunk is within a rigorous rounding bound of the winner are
 //                           re-scanned exactly by their warp.  Output bits are identical.
 //   dcd_fwd_kernel   per pair: shared-memory histograms of idx1/idx2, weights, loss/cd_p/cd_t
@@ -30,9 +30,15 @@
 #include <string.h>
 #include <math.h>
 
+#include <atomic>
+
 #include "ured_chamfer.h"
 
 namespace {
+
+// statistics only (bench.py reports it as gpu_launches); no call's behaviour depends on it
+std::atomic<unsigned long long> g_launches{0};
+#define URED_COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -142,7 +148,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 constexpr int kNNThreads = 128;  // 4 warps, one per SM sub-partition; 5-6 CTAs resident per SM
 constexpr int kTile = 1024;      // candidates per shared-memory stage
 constexpr int kStages = 2;
-constexpr int kChunk = 16;       // candidates per running-minimum chunk (divides 32)
+constexpr int kChunk = 32;       // candidates per running-minimum chunk (= the padding granule of the packed image)
 constexpr float kInf = __builtin_huge_valf();
 
 struct NNParams {
@@ -209,17 +215,17 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
     }
 
     // ---- queries in registers ------------------------------------------------------------
-    float qx[R], qy[R], qz[R];   // EXACT: -q (added to the candidate); SCREEN: -2q (multiplied)
-    float oqx[R], oqy[R], oqz[R];
+    // EXACT keeps -q (added to the candidate), SCREEN keeps -2q (multiplied); both scalings are exact and
+    // are undone after the main loop, so only one copy of the query lives in registers
+    float qx[R], qy[R], qz[R];
     float best[R], second[R];
     int bchunk[R];
+    constexpr float kScale = SCREEN ? -2.0f : -1.0f, kUnscale = SCREEN ? -0.5f : -1.0f;
 #pragma unroll
     for (int r = 0; r < R; r++) {
         int j = (qt * R + r) * kNNThreads + tid;
         j = j < nq ? j : nq - 1;
-        oqx[r] = qxyz[j * 3 + 0]; oqy[r] = qxyz[j * 3 + 1]; oqz[r] = qxyz[j * 3 + 2];
-        const float sc = SCREEN ? -2.0f : -1.0f;
-        qx[r] = sc * oqx[r]; qy[r] = sc * oqy[r]; qz[r] = sc * oqz[r];
+        qx[r] = kScale * qxyz[j * 3 + 0]; qy[r] = kScale * qxyz[j * 3 + 1]; qz[r] = kScale * qxyz[j * 3 + 2];
         best[r] = kInf; second[r] = kInf; bchunk[r] = 0;
     }
 
@@ -295,19 +301,27 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
     const int lane = tid & 31;
 #pragma unroll
     for (int r = 0; r < R; r++) {
+        const float oqx = kUnscale * qx[r], oqy = kUnscale * qy[r], oqz = kUnscale * qz[r];
         const int c = bchunk[r];
         float bd = 0.0f;
         int bi = c;
 #pragma unroll
-        for (int k = 0; k < G; k++) {
+        for (int k = 0; k < G; k += 4) {
             // entries past nc replicate point nc-1 and can therefore never be strictly smaller
-            const float d = exact_d(gX[c + k], gY[c + k], gZ[c + k], oqx[r], oqy[r], oqz[r]);
-            if (k == 0 || d < bd) { bd = d; bi = c + k; }
+            const float4 x4 = *reinterpret_cast<const float4 *>(gX + c + k);
+            const float4 y4 = *reinterpret_cast<const float4 *>(gY + c + k);
+            const float4 z4 = *reinterpret_cast<const float4 *>(gZ + c + k);
+            const float d0 = exact_d(x4.x, y4.x, z4.x, oqx, oqy, oqz), d1 = exact_d(x4.y, y4.y, z4.y, oqx, oqy, oqz);
+            const float d2 = exact_d(x4.z, y4.z, z4.z, oqx, oqy, oqz), d3 = exact_d(x4.w, y4.w, z4.w, oqx, oqy, oqz);
+            if (k == 0 || d0 < bd) { bd = d0; bi = c + k; }
+            if (d1 < bd) { bd = d1; bi = c + k + 1; }
+            if (d2 < bd) { bd = d2; bi = c + k + 2; }
+            if (d3 < bd) { bd = d3; bi = c + k + 3; }
         }
         if (SCREEN) {
             // |s + |q|^2 - d_fp32| <= 11.02 u S^2 with S = |q| + max|c| (DESIGN.md "screening bound");
             // a runner-up chunk farther than twice that cannot hold the argmin.  eps = 32 u S^2.
-            const float qn = __fsqrt_ru(__fmaf_rn(oqz[r], oqz[r], __fmaf_rn(oqy[r], oqy[r], oqx[r] * oqx[r]))) * 1.000001f;
+            const float qn = __fsqrt_ru(__fmaf_rn(oqz, oqz, __fmaf_rn(oqy, oqy, oqx * oqx))) * 1.000001f;
             const float S = qn + cn;
             const float eps = __fmaf_rn(S * S, 1.9073486e-6f /* 2^-19 */, 1e-35f);
             const bool ambiguous = !(second[r] > best[r] + eps);
@@ -315,9 +329,9 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
             while (todo) {
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const float ax = __shfl_sync(0xffffffffu, oqx[r], src);
-                const float ay = __shfl_sync(0xffffffffu, oqy[r], src);
-                const float az = __shfl_sync(0xffffffffu, oqz[r], src);
+                const float ax = __shfl_sync(0xffffffffu, oqx, src);
+                const float ay = __shfl_sync(0xffffffffu, oqy, src);
+                const float az = __shfl_sync(0xffffffffu, oqz, src);
                 float wd = kInf;
                 int wi = 0x7fffffff;
                 for (int k = lane; k < nc; k += 32) {
@@ -543,6 +557,7 @@ int launch_nn(const NNParams &p, int B, cudaStream_t st) {
     const long long grid = (long long)B * (p.qtiles[0] + p.qtiles[1]);
     if (grid > 0x7fffffffll) return fail_arg(URED_E_SHAPE, "too many work items for one launch");
     nn_kernel<SCREEN, R><<<(unsigned)grid, kNNThreads, smem, st>>>(p);
+    URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "nn_kernel launch");
 }
 
@@ -555,6 +570,7 @@ extern "C" {
 
 int ured_abi_version(void) { return URED_ABI_VERSION; }
 const char *ured_last_error_string(void) { return g_err; }
+unsigned long long ured_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 size_t ured_packed_bytes(int count, int n) {
     if (count <= 0 || n <= 0) return 256;
@@ -568,6 +584,7 @@ int ured_pack_clouds(const float *xyz, int count, int n, void *packed, void *str
     if ((uintptr_t)packed % 256) return fail_arg(URED_E_WORKSPACE, "packed image must be 256-byte aligned");
     PackedView v = view_packed(packed, count, n);
     pack_kernel<<<count, kPackThreads, 0, (cudaStream_t)stream>>>(xyz, n, v.np, (float *)v.soa, (float *)v.wmax);
+    URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "pack_kernel launch");
 }
 
@@ -649,6 +666,7 @@ int ured_dcd_forward(const float *dist1, const float *dist2, const int *idx1, co
     }
     dcd_fwd_kernel<<<B, kDcdThreads, smem, (cudaStream_t)stream>>>(dist1, dist2, idx1, idx2, n1, n2, alpha, n_lambda, frac_12,
                                                                    frac_21, loss, cd_p, cd_t, ew1, ew2);
+    URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "dcd_fwd_kernel launch");
 }
 
@@ -689,8 +707,10 @@ int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n
     else if (shared1 && !shared2) grad_kernel<0, true, false><<<grid, kGradThreads, 0, st>>>(p);
     else if (!shared1 && shared2) grad_kernel<0, false, true><<<grid, kGradThreads, 0, st>>>(p);
     else grad_kernel<0, true, true><<<grid, kGradThreads, 0, st>>>(p);
+    URED_COUNT_LAUNCH();
     URED_CUDA(cudaGetLastError(), "grad_kernel<own> launch");
     grad_kernel<1, false, false><<<grid, kGradThreads, 0, st>>>(p);
+    URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "grad_kernel<scatter> launch");
 }
 
@@ -708,6 +728,7 @@ int ured_topk_smallest(const float *scores, int rows, int cols, int k, int idx_o
     if (rows == 0 || k == 0) return 0;
     if (!scores || !out_scores || !out_idx) return fail_arg(URED_E_NULL, "ured_topk_smallest: NULL pointer");
     topk_kernel<<<rows, kTopkThreads, 0, (cudaStream_t)stream>>>(scores, cols, k, idx_offset, out_scores, out_idx);
+    URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "topk_kernel launch");
 }
 

@@ -11,6 +11,8 @@ both clouds.  Differences, all deliberate:
   * idx1/idx2 are marked non-differentiable.
 GPU tensors only, as in the reference (:25) -- there is no CPU fallback.
 """
+import os
+
 import torch
 from torch import nn
 from torch.autograd import Function
@@ -32,9 +34,15 @@ def _stream(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def nn_forward(xyz1, xyz2, exact_only=False):
-    """Raw forward: (dist1, dist2, idx1, idx2) for contiguous float32 CUDA clouds."""
+def nn_forward(xyz1, xyz2, exact_only=None):
+    """Raw forward: (dist1, dist2, idx1, idx2) for contiguous float32 CUDA clouds.
+
+    ``exact_only`` selects the difference-form kernel on every pair instead of screen + exact re-check
+    (same output bits; default from the URED_EXACT_ONLY=1 environment knob, used for A/B timing).
+    """
     lib = _native.load()
+    if exact_only is None:
+        exact_only = os.environ.get("URED_EXACT_ONLY", "0") == "1"
     B, n, _ = xyz1.shape
     m = xyz2.shape[1]
     if xyz2.shape[0] != B:

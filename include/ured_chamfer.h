@@ -62,6 +62,8 @@ extern "C" {
 
 int ured_abi_version(void);
 const char *ured_last_error_string(void);
+/* number of kernels this library has launched in this process so far (statistics only) */
+unsigned long long ured_kernel_launches(void);
 
 /* ---- packed clouds ---------------------------------------------------------------------
  * The nearest-neighbour kernel stages the opposing cloud through shared memory with TMA bulk
