@@ -290,8 +290,10 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
                 bchunk[r] = better ? chunk_id : bchunk[r];
             }
         }
-        __syncthreads();  // every thread is done with stage s
-        if (tid == 0 && t + kStages < ntiles) issue_tile(t + kStages);
+        if (t + kStages < ntiles) {  // the stage is reused: wait until every thread is done reading it
+            __syncthreads();
+            if (tid == 0) issue_tile(t + kStages);
+        }
     }
 
     // ---- exact resolution of the winning chunk ---------------------------------------------
@@ -360,16 +362,6 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
 // ------------------------------------------------------------------------------------------
 constexpr int kDcdThreads = 512;
 
-__device__ __forceinline__ double block_sum(double v, double *red) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double s = 0.0;
-    for (int i = 0; i < kDcdThreads / 32; i++) s += red[i];  // fixed order: deterministic
-    return s;
-}
-
 // torch's pow(tensor, python scalar) special cases (ATen pow_tensor_scalar): 1 -> x, 2 -> x*x,
 // 0.5 -> sqrt, 0 -> 1; anything else goes through powf
 __device__ __forceinline__ float pow_lambda(float c, float n_lambda) {
@@ -388,7 +380,7 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
                                                               float *__restrict__ cd_t, float *__restrict__ ew1,
                                                               float *__restrict__ ew2) {
     extern __shared__ int hist[];  // count1[n2] | count2[n1]
-    __shared__ double red[kDcdThreads / 32];
+    __shared__ double red[(kDcdThreads / 32) * 6];
     int *count1 = hist, *count2 = hist + n2;
     const size_t b = blockIdx.x;
     const float *d1 = dist1 + b * n1, *d2 = dist2 + b * n2;
@@ -399,7 +391,9 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
     for (int k = threadIdx.x; k < n2; k += kDcdThreads) atomicAdd(&count2[i2[k]], 1);
     __syncthreads();
 
-    double s_term[2], s_d[2], s_sqrt[2];
+    // per-thread float64 partial sums: [side][term, d, sqrt d]; reduced once (warp shuffles, then a fixed-order
+    // pass over the per-warp partials, so the result is deterministic)
+    double part[6];
 #pragma unroll
     for (int side = 0; side < 2; side++) {
         const int n = side ? n2 : n1;
@@ -421,9 +415,23 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
             a_d += (double)dk;
             a_sqrt += (double)sqrtf(dk);
         }
-        s_term[side] = block_sum(a_term, red);
-        s_d[side] = block_sum(a_d, red);
-        s_sqrt[side] = block_sum(a_sqrt, red);
+        part[side * 3 + 0] = a_term; part[side * 3 + 1] = a_d; part[side * 3 + 2] = a_sqrt;
+    }
+#pragma unroll
+    for (int v = 0; v < 6; v++)
+        for (int o = 16; o > 0; o >>= 1) part[v] += __shfl_xor_sync(0xffffffffu, part[v], o);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int v = 0; v < 6; v++) red[(threadIdx.x >> 5) * 6 + v] = part[v];
+    }
+    __syncthreads();
+    double s_term[2], s_d[2], s_sqrt[2];
+    if (threadIdx.x == 0) {
+        double tot[6] = {0, 0, 0, 0, 0, 0};
+        for (int w = 0; w < kDcdThreads / 32; w++)
+            for (int v = 0; v < 6; v++) tot[v] += red[w * 6 + v];
+        s_term[0] = tot[0]; s_d[0] = tot[1]; s_sqrt[0] = tot[2];
+        s_term[1] = tot[3]; s_d[1] = tot[4]; s_sqrt[1] = tot[5];
     }
     if (threadIdx.x == 0) {
         const float loss1 = (float)(s_term[0] / n1), loss2 = (float)(s_term[1] / n2);
@@ -453,6 +461,8 @@ struct GradParams {
     float alpha;
 };
 
+__device__ __forceinline__ float point_grad_coeff(const GradParams &p, int side, size_t b, size_t pt, int n_own);
+
 // PHASE 0: own-side terms, plain coalesced stores (every output element is written exactly once
 //          when rep1 == 1 / mod2 == B; broadcast clouds fall back to atomics on a zeroed buffer)
 // PHASE 1: scatter-side terms, red.global.add.f32 keyed on idx
@@ -468,11 +478,7 @@ __global__ void __launch_bounds__(kGradThreads) grad_kernel(const GradParams p) 
         const size_t c_own = side ? c2 : c1, c_oth = side ? c1 : c2;
         const size_t pt = b * n_own + j;
         // upstream gradient w.r.t. this point's squared NN distance
-        const float *g_dist = side ? p.g_dist[1] : p.g_dist[0];
-        float gd = g_dist ? g_dist[pt] : 0.0f;
-        if (p.g_cd_t) gd += p.g_cd_t[b] / (float)n_own;
-        if (p.g_cd_p) gd += p.g_cd_p[b] * 0.5f / (float)n_own * (0.5f / sqrtf((side ? p.dist[1] : p.dist[0])[pt]));
-        if (p.g_loss) gd += p.g_loss[b] * 0.5f / (float)n_own * (p.alpha * (side ? p.ew[1] : p.ew[0])[pt]);
+        const float gd = point_grad_coeff(p, side, b, pt, n_own);
         const int j2 = (side ? p.idx[1] : p.idx[0])[pt];
         const float *a = (side ? p.xyz[1] : p.xyz[0]) + (c_own * n_own + j) * 3;
         const float *o = (side ? p.xyz[0] : p.xyz[1]) + (c_oth * n_oth + j2) * 3;
@@ -493,6 +499,52 @@ __global__ void __launch_bounds__(kGradThreads) grad_kernel(const GradParams p) 
             atomicAdd(dst + 0, -gx); atomicAdd(dst + 1, -gy); atomicAdd(dst + 2, -gz);
         }
     }
+}
+
+// One CTA per pair, both clouds' gradients accumulated in shared memory (own-side and scatter-side
+// terms alike), then written out once, coalesced: no global atomics, no zero-fill, one launch.
+// Used when the pair's (n1 + n2) * 12 bytes fit in shared memory and neither cloud is broadcast.
+constexpr int kGradSmemThreads = 512;
+
+__device__ __forceinline__ float point_grad_coeff(const GradParams &p, int side, size_t b, size_t pt, int n_own) {
+    const float *g_dist = side ? p.g_dist[1] : p.g_dist[0];
+    float gd = g_dist ? g_dist[pt] : 0.0f;
+    if (p.g_cd_t) gd += p.g_cd_t[b] / (float)n_own;
+    if (p.g_cd_p) gd += p.g_cd_p[b] * 0.5f / (float)n_own * (0.5f / sqrtf((side ? p.dist[1] : p.dist[0])[pt]));
+    if (p.g_loss) gd += p.g_loss[b] * 0.5f / (float)n_own * (p.alpha * (side ? p.ew[1] : p.ew[0])[pt]);
+    return gd;
+}
+
+__global__ void __launch_bounds__(kGradSmemThreads) grad_smem_kernel(const GradParams p) {
+    extern __shared__ float acc[];  // grad of cloud 1 [n1*3] | grad of cloud 2 [n2*3]
+    const size_t b = blockIdx.x;
+    const int n1 = p.n[0], n2 = p.n[1];
+    const int total3 = (n1 + n2) * 3;
+    for (int k = threadIdx.x; k < total3; k += kGradSmemThreads) acc[k] = 0.0f;
+    __syncthreads();
+    const float *xyz1 = p.xyz[0] + b * n1 * 3, *xyz2 = p.xyz[1] + b * n2 * 3;
+    for (int t = threadIdx.x; t < n1 + n2; t += kGradSmemThreads) {
+        const int side = t >= n1 ? 1 : 0;
+        const int j = side ? t - n1 : t;
+        const int n_own = side ? n2 : n1;
+        const size_t pt = b * n_own + j;
+        const float gd = point_grad_coeff(p, side, b, pt, n_own);
+        const int j2 = (side ? p.idx[1] : p.idx[0])[pt];
+        const float *a = (side ? xyz2 : xyz1) + j * 3;
+        const float *o = (side ? xyz1 : xyz2) + j2 * 3;
+        const float g = __fmul_rn(gd, 2.0f);  // chamfer3D.cu:166
+        const float gx = __fmul_rn(g, __fsub_rn(a[0], o[0]));
+        const float gy = __fmul_rn(g, __fsub_rn(a[1], o[1]));
+        const float gz = __fmul_rn(g, __fsub_rn(a[2], o[2]));
+        float *own = acc + (side ? n1 * 3 : 0) + j * 3;
+        float *oth = acc + (side ? 0 : n1 * 3) + j2 * 3;
+        atomicAdd(own + 0, gx); atomicAdd(own + 1, gy); atomicAdd(own + 2, gz);
+        atomicAdd(oth + 0, -gx); atomicAdd(oth + 1, -gy); atomicAdd(oth + 2, -gz);
+    }
+    __syncthreads();
+    float *g1 = p.grad[0] + b * n1 * 3, *g2 = p.grad[1] + b * n2 * 3;
+    for (int k = threadIdx.x; k < n1 * 3; k += kGradSmemThreads) g1[k] = acc[k];
+    for (int k = threadIdx.x; k < n2 * 3; k += kGradSmemThreads) g2[k] = acc[n1 * 3 + k];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -699,6 +751,17 @@ int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n
     p.n[0] = n1; p.n[1] = n2;
     p.rep1 = rep1; p.mod2 = mod2;
     p.alpha = alpha;
+    const size_t smem_need = (size_t)(n1 + n2) * 3 * sizeof(float);
+    if (!shared1 && !shared2 && smem_need <= 96 * 1024) {
+        static thread_local bool attr_done = false;
+        if (!attr_done) {
+            URED_CUDA(cudaFuncSetAttribute(grad_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "grad smem attribute");
+            attr_done = true;
+        }
+        grad_smem_kernel<<<B, kGradSmemThreads, smem_need, st>>>(p);
+        URED_COUNT_LAUNCH();
+        return check_cuda(cudaGetLastError(), "grad_smem_kernel launch");
+    }
     int gx = (n1 + n2 + kGradThreads - 1) / kGradThreads;
     if (gx > 64) gx = 64;
     if (B > 65535) return fail_arg(URED_E_SHAPE, "ured_dcd_backward: B > 65535 pairs per call");
