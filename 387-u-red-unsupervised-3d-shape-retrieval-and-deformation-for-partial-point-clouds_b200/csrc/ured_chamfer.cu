@@ -161,6 +161,12 @@ struct NNParams {
     int np[2];
     int qtiles[2];  // query tiles per pair for direction 0 / 1
     int rep1, mod2;
+    // candidate splitting: with nsplit > 1 every (pair, direction, query tile) is cut into nsplit CTAs, each
+    // scanning a contiguous candidate range and writing its exact partial (d, idx) to part_*[split][B][n]
+    int nsplit;
+    int B;
+    float *part_dist[2];
+    int *part_idx[2];
 };
 
 // the reference's pair arithmetic (chamfer3D.cu:32-35 as compiled by nvcc 12.9 for sm_100a):
@@ -179,9 +185,11 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
 
     const int tid = threadIdx.x;
     // ---- work item: (pair b, direction, query tile) --------------------------------------
-    const int per_pair = p.qtiles[0] + p.qtiles[1];
+    const int per_pair = (p.qtiles[0] + p.qtiles[1]) * p.nsplit;
     const int b = blockIdx.x / per_pair;
-    const int rem = blockIdx.x - b * per_pair;
+    const int rem0 = blockIdx.x - b * per_pair;
+    const int sp = rem0 % p.nsplit;  // candidate split handled by this CTA
+    const int rem = rem0 / p.nsplit;
     const int dir = rem >= p.qtiles[0] ? 1 : 0;
     const int qt = dir ? rem - p.qtiles[0] : rem;
     const int c1 = b / p.rep1, c2 = b % p.mod2;
@@ -191,12 +199,17 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
     const float *__restrict__ qxyz = (dir ? p.xyz[1] : p.xyz[0]) + (size_t)cq * nq * 3;
     const float *__restrict__ csoa = (dir ? p.soa[0] : p.soa[1]) + (size_t)cc * ncp * 4;
 
+    // candidate range of this split, in whole 32-candidate chunks
+    const int chunks_per_split = (ncp / kChunk + p.nsplit - 1) / p.nsplit;
+    const int k_lo = min(ncp, sp * chunks_per_split * kChunk);
+    const int k_hi = min(ncp, k_lo + chunks_per_split * kChunk);
+
     // ---- pipeline prologue ---------------------------------------------------------------
-    const int ntiles = (ncp + kTile - 1) / kTile;
+    const int ntiles = (k_hi - k_lo + kTile - 1) / kTile;
     auto issue_tile = [&](int t) {
         const int s = t % kStages;
-        const int k0 = t * kTile;
-        const int tk = min(kTile, ncp - k0);
+        const int k0 = k_lo + t * kTile;
+        const int tk = min(kTile, k_hi - k0);
         const uint32_t bytes = (uint32_t)tk * sizeof(float);
         mbar_arrive_expect_tx(&full_bar[s], bytes * NARR);
 #pragma unroll
@@ -210,7 +223,7 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
     }
     __syncthreads();
     if (tid == 0) {
-        issue_tile(0);
+        if (ntiles > 0) issue_tile(0);
         if (ntiles > 1) issue_tile(1);
     }
 
@@ -226,14 +239,14 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
         int j = (qt * R + r) * kNNThreads + tid;
         j = j < nq ? j : nq - 1;
         qx[r] = kScale * qxyz[j * 3 + 0]; qy[r] = kScale * qxyz[j * 3 + 1]; qz[r] = kScale * qxyz[j * 3 + 2];
-        best[r] = kInf; second[r] = kInf; bchunk[r] = 0;
+        best[r] = kInf; second[r] = kInf; bchunk[r] = k_lo;
     }
 
     // ---- main loop over candidate tiles ----------------------------------------------------
     for (int t = 0; t < ntiles; t++) {
         const int s = t % kStages;
-        const int k0 = t * kTile;
-        const int tk = min(kTile, ncp - k0);
+        const int k0 = k_lo + t * kTile;
+        const int tk = min(kTile, k_hi - k0);
         mbar_wait(&full_bar[s], (uint32_t)(t / kStages) & 1u);
         const float *X = stage_mem + (s * NARR + 0) * kTile;
         const float *Y = stage_mem + (s * NARR + 1) * kTile;
@@ -304,7 +317,7 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const float oqx = kUnscale * qx[r], oqy = kUnscale * qy[r], oqz = kUnscale * qz[r];
-        const int c = bchunk[r];
+        const int c = min(bchunk[r], ncp - G);  // (an empty trailing split re-reads the last chunk; its result loses every merge)
         float bd = 0.0f;
         int bi = c;
 #pragma unroll
@@ -336,7 +349,7 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
                 const float az = __shfl_sync(0xffffffffu, oqz, src);
                 float wd = kInf;
                 int wi = 0x7fffffff;
-                for (int k = lane; k < nc; k += 32) {
+                for (int k = k_lo + lane; k < min(k_hi, nc); k += 32) {
                     const float d = exact_d(gX[k], gY[k], gZ[k], ax, ay, az);
                     if (d < wd || wi == 0x7fffffff) { wd = d; wi = k; }
                 }
@@ -351,10 +364,53 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
         }
         const int j = (qt * R + r) * kNNThreads + tid;
         if (j < nq) {
-            (dir ? p.dist[1] : p.dist[0])[(size_t)b * nq + j] = bd;
-            (dir ? p.idx[1] : p.idx[0])[(size_t)b * nq + j] = bi;
+            if (p.nsplit == 1) {
+                (dir ? p.dist[1] : p.dist[0])[(size_t)b * nq + j] = bd;
+                (dir ? p.idx[1] : p.idx[0])[(size_t)b * nq + j] = bi;
+            } else {
+                if (k_lo >= k_hi) bd = kInf;  // empty split
+                const size_t o = ((size_t)sp * p.B + b) * nq + j;
+                (dir ? p.part_dist[1] : p.part_dist[0])[o] = bd;
+                (dir ? p.part_idx[1] : p.part_idx[0])[o] = bi;
+            }
         }
     }
+}
+
+// Merge of the per-split partial results: splits cover ascending candidate ranges, so a strict '<' in split
+// order keeps the lowest index among equal distances -- the same rule as the reference's tile merge (chamfer3D.cu:126).
+__global__ void __launch_bounds__(256) merge_splits_kernel(const float *__restrict__ pd, const int *__restrict__ pi, size_t total,
+                                                           int nsplit, float *__restrict__ dist, int *__restrict__ idx) {
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= total) return;
+    float d = pd[t];
+    int i = pi[t];
+    for (int s = 1; s < nsplit; s++) {
+        const float ds = pd[s * total + t];
+        if (ds < d) { d = ds; i = pi[s * total + t]; }
+    }
+    dist[t] = d;
+    idx[t] = i;
+}
+
+// Launch shape: R queries per thread and nsplit candidate splits, chosen so that the grid has several waves of
+// CTAs (148 SMs x ~6 resident CTAs) without cutting the candidate range below 512 points per CTA.
+struct NNShape { int R; int nsplit; };
+NNShape choose_nn_shape(int B, int n1, int n2) {
+    auto items = [&](int R) {
+        return (long long)B * ((n1 + R * kNNThreads - 1) / (R * kNNThreads) + (n2 + R * kNNThreads - 1) / (R * kNNThreads));
+    };
+    NNShape sh;
+    sh.R = 4;
+    sh.nsplit = 1;
+    const long long want = 148ll * 6 * 4;
+    const int max_split = (n1 < n2 ? n1 : n2) / 512;
+    if (items(4) < want) {
+        long long need = (want + items(4) - 1) / items(4);
+        while (sh.nsplit < need && sh.nsplit * 2 <= max_split && sh.nsplit < 8) sh.nsplit *= 2;
+        if (items(4) * sh.nsplit < 148ll * 4) sh.R = 2;
+    }
+    return sh;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -606,7 +662,7 @@ template <bool SCREEN, int R>
 int launch_nn(const NNParams &p, int B, cudaStream_t st) {
     constexpr int NARR = SCREEN ? 4 : 3;
     const size_t smem = (size_t)kStages * NARR * kTile * sizeof(float);
-    const long long grid = (long long)B * (p.qtiles[0] + p.qtiles[1]);
+    const long long grid = (long long)B * (p.qtiles[0] + p.qtiles[1]) * p.nsplit;
     if (grid > 0x7fffffffll) return fail_arg(URED_E_SHAPE, "too many work items for one launch");
     nn_kernel<SCREEN, R><<<(unsigned)grid, kNNThreads, smem, st>>>(p);
     URED_COUNT_LAUNCH();
@@ -640,8 +696,15 @@ int ured_pack_clouds(const float *xyz, int count, int n, void *packed, void *str
     return check_cuda(cudaGetLastError(), "pack_kernel launch");
 }
 
+size_t ured_nn_scratch_bytes(int B, int n1, int n2) {
+    if (B <= 0 || n1 <= 0 || n2 <= 0) return 0;
+    const NNShape sh = choose_nn_shape(B, n1, n2);
+    return sh.nsplit > 1 ? align_up((size_t)sh.nsplit * B * ((size_t)n1 + n2) * 8, 256) : 0;
+}
+
 int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *xyz2, const void *packed2, int n2, int B,
-                   int rep1, int mod2, float *dist1, float *dist2, int *idx1, int *idx2, unsigned flags, void *stream) {
+                   int rep1, int mod2, float *dist1, float *dist2, int *idx1, int *idx2, void *scratch, size_t scratch_bytes,
+                   unsigned flags, void *stream) {
     int rc = check_pairs(B, n1, n2, rep1, mod2);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -665,19 +728,40 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
     p.n[0] = n1; p.n[1] = n2;
     p.np[0] = v1.np; p.np[1] = v2.np;
     p.rep1 = rep1; p.mod2 = mod2;
-    // queries per CTA: 4 per thread when that still leaves every SM several CTAs, else 2
     const bool exact = (flags & URED_FLAG_EXACT_ONLY) != 0;
-    const long long items4 = (long long)B * ((n1 + 4 * kNNThreads - 1) / (4 * kNNThreads) + (n2 + 4 * kNNThreads - 1) / (4 * kNNThreads));
-    const int R = items4 >= 148 * 8 ? 4 : 2;
+    const NNShape sh = choose_nn_shape(B, n1, n2);
+    const int R = sh.R;
     p.qtiles[0] = (n1 + R * kNNThreads - 1) / (R * kNNThreads);
     p.qtiles[1] = (n2 + R * kNNThreads - 1) / (R * kNNThreads);
-    if (exact) return R == 4 ? launch_nn<false, 4>(p, B, st) : launch_nn<false, 2>(p, B, st);
-    return R == 4 ? launch_nn<true, 4>(p, B, st) : launch_nn<true, 2>(p, B, st);
+    p.nsplit = sh.nsplit;
+    p.B = B;
+    const size_t tot1 = (size_t)B * n1, tot2 = (size_t)B * n2;
+    if (sh.nsplit > 1) {
+        if (!scratch) return fail_arg(URED_E_NULL, "ured_nn_packed: scratch buffer required for this shape (ured_nn_scratch_bytes)");
+        if ((uintptr_t)scratch % 256 || scratch_bytes < ured_nn_scratch_bytes(B, n1, n2))
+            return fail_arg(URED_E_WORKSPACE, "ured_nn_packed: scratch too small or misaligned");
+        // [dist1 parts | dist2 parts | idx1 parts | idx2 parts]
+        p.part_dist[0] = (float *)scratch;
+        p.part_dist[1] = p.part_dist[0] + sh.nsplit * tot1;
+        p.part_idx[0] = (int *)(p.part_dist[1] + sh.nsplit * tot2);
+        p.part_idx[1] = p.part_idx[0] + sh.nsplit * tot1;
+    } else {
+        p.part_dist[0] = p.part_dist[1] = nullptr;
+        p.part_idx[0] = p.part_idx[1] = nullptr;
+    }
+    if (exact) rc = R == 4 ? launch_nn<false, 4>(p, B, st) : launch_nn<false, 2>(p, B, st);
+    else rc = R == 4 ? launch_nn<true, 4>(p, B, st) : launch_nn<true, 2>(p, B, st);
+    if (rc || sh.nsplit == 1) return rc;
+    merge_splits_kernel<<<(unsigned)((tot1 + 255) / 256), 256, 0, st>>>(p.part_dist[0], p.part_idx[0], tot1, sh.nsplit, dist1, idx1);
+    URED_COUNT_LAUNCH();
+    merge_splits_kernel<<<(unsigned)((tot2 + 255) / 256), 256, 0, st>>>(p.part_dist[1], p.part_idx[1], tot2, sh.nsplit, dist2, idx2);
+    URED_COUNT_LAUNCH();
+    return check_cuda(cudaGetLastError(), "merge_splits_kernel launch");
 }
 
 size_t ured_chamfer_workspace_bytes(int B, int n1, int n2) {
     if (B < 0) B = 0;
-    return ured_packed_bytes(B, n1) + ured_packed_bytes(B, n2);
+    return ured_packed_bytes(B, n1) + ured_packed_bytes(B, n2) + ured_nn_scratch_bytes(B, n1, n2);
 }
 
 int ured_chamfer_forward(const float *xyz1, const float *xyz2, int B, int n1, int n2, float *dist1, float *dist2, int *idx1,
@@ -699,7 +783,9 @@ int ured_chamfer_forward(const float *xyz1, const float *xyz2, int B, int n1, in
         rc = ured_pack_clouds(xyz2, B, n2, pk2, stream);
         if (rc) return rc;
     }
-    return ured_nn_packed(xyz1, pk1, n1, xyz2, pk2, n2, B, 1, B, dist1, dist2, idx1, idx2, flags, stream);
+    void *scratch = (char *)pk2 + ured_packed_bytes(B, n2);
+    return ured_nn_packed(xyz1, pk1, n1, xyz2, pk2, n2, B, 1, B, dist1, dist2, idx1, idx2, scratch,
+                          ured_nn_scratch_bytes(B, n1, n2), flags, stream);
 }
 
 int ured_dcd_forward(const float *dist1, const float *dist2, const int *idx1, const int *idx2, int B, int n1, int n2,

@@ -65,12 +65,14 @@ def nn_pairs(cloud1, cloud2, B, rep1, mod2, first2=0, count2=None, exact_only=Fa
     if first2 != 0:
         raise ValueError("pack each library shard separately (first2 must be 0)")
     flags = _native.URED_FLAG_EXACT_ONLY if exact_only else 0
+    scratch_bytes = lib.ured_nn_scratch_bytes(B, n1, n2)
+    scratch = torch.empty(scratch_bytes, device=dev, dtype=torch.uint8) if scratch_bytes else None
     with torch.cuda.device(dev):
         rc = lib.ured_nn_packed(_native.ptr(c1.xyz), _native.ptr(c1.packed), n1,
                                 _native.ptr(c2.xyz), _native.ptr(c2.packed), n2,
                                 B, rep1, mod2,
                                 _native.ptr(dist1), _native.ptr(dist2), _native.ptr(idx1), _native.ptr(idx2),
-                                flags, _stream(dev))
+                                _native.ptr(scratch), scratch_bytes, flags, _stream(dev))
     _native.check(rc, "ured_nn_packed")
     return dist1, dist2, idx1, idx2
 

@@ -305,10 +305,14 @@ def main():
     stream = torch.cuda.current_stream(dev).cuda_stream
     flags = 1 if args.exact_only else 0
 
+    scratch_bytes = lib.ured_nn_scratch_bytes(B, n_gt, n_x)
+    scratch = torch.empty(max(scratch_bytes, 256), dtype=torch.uint8, device=dev)
+
     def nn_only():
         rc = lib.ured_nn_packed(gt_dev.data_ptr(), pk_gt.packed.data_ptr(), n_gt,
                                 x_dev.data_ptr(), pk_x.packed.data_ptr(), n_x, B, 1, B,
-                                d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(), flags, stream)
+                                d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
+                                scratch.data_ptr(), scratch_bytes, flags, stream)
         ured._native.check(rc, "ured_nn_packed")
 
     ms_nn, _ = timed(nn_only, args.steps, args.warmup)

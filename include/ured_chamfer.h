@@ -21,7 +21,7 @@
  *
  * Conventions (all entry points)
  *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
- *     (the library never allocates or frees device memory and keeps no global state);
+ *     (the library never allocates or frees device memory; its only global state is a launch counter);
  *   - clouds are row-major contiguous float32 [count, n, 3]; distances float32; indices int32
  *     (same dtypes as the reference: dist_chamfer_3D.py:33-37);
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it
@@ -77,11 +77,17 @@ int ured_pack_clouds(const float *xyz, int count, int n, void *packed, void *str
 /* ---- nearest neighbours on packed clouds (both directions, one launch) --------------------
  * dist1/idx1: [B, n1]  for every point of cloud 1, squared distance to / index of its nearest
  *                      point in cloud 2 (lowest index on ties);  dist2/idx2: [B, n2] vice versa.
- * Results are bit-identical to NmDistanceKernel (chamfer3D.cu:12-134) for finite inputs. */
+ * Results are bit-identical to NmDistanceKernel (chamfer3D.cu:12-134) for finite inputs.
+ *
+ * For shapes whose grid would be too small (few pairs, or very large clouds) the candidate range is split over
+ * several CTAs and merged afterwards; that needs `scratch`: ured_nn_scratch_bytes(B, n1, n2) bytes (0 for most
+ * shapes, in which case scratch may be NULL), 256-byte aligned. */
+size_t ured_nn_scratch_bytes(int B, int n1, int n2);
 int ured_nn_packed(const float *xyz1, const void *packed1, int n1,
                    const float *xyz2, const void *packed2, int n2,
                    int B, int rep1, int mod2,
                    float *dist1, float *dist2, int *idx1, int *idx2,
+                   void *scratch, size_t scratch_bytes,
                    unsigned flags, void *stream);
 
 /* ---- drop-in for chamfer_3D.forward ---------------------------------------------------------

@@ -33,7 +33,9 @@ def test_abi_version_and_sizes(ured):
     # 2 clouds of 2048 points: 2 * 4 arrays * 2048 floats, plus one max-norm float per cloud, 256-aligned
     assert lib.ured_packed_bytes(2, 2048) == 2 * 4 * 2048 * 4 + 256
     assert lib.ured_packed_bytes(1, 100) == 4 * 128 * 4 + 256  # padded to 32 points
-    assert lib.ured_chamfer_workspace_bytes(3, 100, 200) == lib.ured_packed_bytes(3, 100) + lib.ured_packed_bytes(3, 200)
+    assert lib.ured_chamfer_workspace_bytes(3, 100, 200) == lib.ured_packed_bytes(3, 100) + lib.ured_packed_bytes(3, 200) + lib.ured_nn_scratch_bytes(3, 100, 200)
+    assert lib.ured_nn_scratch_bytes(640, 2048, 2048) == 0            # enough pairs: no candidate splitting
+    assert lib.ured_nn_scratch_bytes(16, 16384, 16384) == 4 * 16 * 32768 * 8  # dense clouds: 4 splits of partial (d, idx)
 
 
 def test_argument_errors_do_not_need_a_device(ured):
@@ -42,7 +44,7 @@ def test_argument_errors_do_not_need_a_device(ured):
     assert lib.ured_chamfer_forward(None, None, 2, 8, 8, None, None, None, None, None, 0, 0, None) == E_NULL
     assert b"NULL" in lib.ured_last_error_string()
     assert lib.ured_chamfer_forward(None, None, -1, 8, 8, None, None, None, None, None, 0, 0, None) == E_SHAPE
-    assert lib.ured_nn_packed(None, None, 8, None, None, 8, 4, 0, 4, None, None, None, None, 0, None) == E_SHAPE
+    assert lib.ured_nn_packed(None, None, 8, None, None, 8, 4, 0, 4, None, None, None, None, None, 0, 0, None) == E_SHAPE
     assert lib.ured_topk_smallest(None, 1, 5, 6, 0, None, None, None) == E_RANGE
     assert lib.ured_dcd_forward(None, None, None, None, 1, 8, 8, 1.0, 1.0, 1.0, 1.0, None, None, None, None, None, None) == E_NULL
     # empty batches are a successful no-op
