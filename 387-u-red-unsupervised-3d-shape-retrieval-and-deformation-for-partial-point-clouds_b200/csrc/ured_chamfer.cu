@@ -68,13 +68,17 @@ inline int pad32(int n) { return (n + 31) / 32 * 32; }
 // ------------------------------------------------------------------------------------------
 constexpr int kPackThreads = 256;
 
-// one CTA per cloud; writes X|Y|Z|W (each np floats) and max W
+constexpr int kPackTail = 32;  // floats after X|Y|Z|W of each cloud: [0] = max W, rest unused (keeps blocks 128-byte aligned)
+inline size_t cloud_stride(int np) { return (size_t)np * 4 + kPackTail; }
+
+// one CTA per cloud; writes the cloud's block X|Y|Z|W (each np floats) | tail (max W)
 __global__ void __launch_bounds__(kPackThreads) pack_kernel(const float *__restrict__ xyz, int n, int np,
-                                                            float *__restrict__ soa, float *__restrict__ wmax) {
+                                                            float *__restrict__ soa) {
     const size_t cloud = blockIdx.x;
     const float *src = xyz + cloud * (size_t)n * 3;
-    float *X = soa + cloud * (size_t)np * 4;
+    float *X = soa + cloud * ((size_t)np * 4 + kPackTail);
     float *Y = X + np, *Z = Y + np, *W = Z + np;
+    float *wmax = W + np;
     float m = 0.0f;
     for (int k = threadIdx.x; k < np; k += kPackThreads) {
         int ks = k < n ? k : n - 1;  // padding replicates the last point: it can tie with it, never beat it
@@ -90,20 +94,18 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const float *__restr
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < kPackThreads / 32; i++) m = fmaxf(m, red[i]);
-        wmax[cloud] = m;
+        wmax[0] = m;
     }
 }
 
 struct PackedView {
-    const float *soa;   // count * 4 * np floats
-    const float *wmax;  // count floats
+    const float *soa;  // count blocks of cloud_stride(np) floats; any sub-range of clouds is itself a packed image
     int np;
 };
-PackedView view_packed(const void *packed, int count, int n) {
+PackedView view_packed(const void *packed, int n) {
     PackedView v;
     v.np = pad32(n);
     v.soa = (const float *)packed;
-    v.wmax = (const float *)((const char *)packed + align_up((size_t)count * 4 * v.np * sizeof(float), 256));
     return v;
 }
 
@@ -154,7 +156,6 @@ constexpr float kInf = __builtin_huge_valf();
 struct NNParams {
     const float *xyz[2];   // raw clouds (queries are read from here)
     const float *soa[2];   // packed images (candidates are streamed from here)
-    const float *wmax[2];  // max |p|^2 per cloud
     float *dist[2];
     int *idx[2];
     int n[2];
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
     // (ternaries, not p.x[dir]: dynamic indexing would copy the parameter block to local memory)
     const int nq = dir ? p.n[1] : p.n[0], nc = dir ? p.n[0] : p.n[1], ncp = dir ? p.np[0] : p.np[1];
     const float *__restrict__ qxyz = (dir ? p.xyz[1] : p.xyz[0]) + (size_t)cq * nq * 3;
-    const float *__restrict__ csoa = (dir ? p.soa[0] : p.soa[1]) + (size_t)cc * ncp * 4;
+    const float *__restrict__ csoa = (dir ? p.soa[0] : p.soa[1]) + (size_t)cc * ((size_t)ncp * 4 + kPackTail);
 
     // candidate range of this split, in whole 32-candidate chunks
     const int chunks_per_split = (ncp / kChunk + p.nsplit - 1) / p.nsplit;
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
     // ---- exact resolution of the winning chunk ---------------------------------------------
     const float *__restrict__ gX = csoa, *__restrict__ gY = csoa + ncp, *__restrict__ gZ = csoa + 2 * (size_t)ncp;
     float cn = 0.0f;
-    if (SCREEN) cn = __fsqrt_ru((dir ? p.wmax[0] : p.wmax[1])[cc]) * 1.000001f;
+    if (SCREEN) cn = __fsqrt_ru(csoa[(size_t)ncp * 4]) * 1.000001f;  // max W of the candidate cloud (block tail)
     const int lane = tid & 31;
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -614,31 +615,46 @@ __device__ __forceinline__ unsigned long long score_key(float s, int i) {
     return ((unsigned long long)u << 32) | (unsigned)i;
 }
 
-__global__ void __launch_bounds__(kTopkThreads) topk_kernel(const float *__restrict__ scores, int cols, int k, int idx_offset,
-                                                            float *__restrict__ out_scores, int *__restrict__ out_idx) {
+// ids == nullptr: rank columns by (score, column) and report column + idx_offset;
+// ids != nullptr: rank by (score, ids[column]) and report the id (merge of per-shard lists); ids < 0 are padding.
+__global__ void __launch_bounds__(kTopkThreads) topk_kernel(const float *__restrict__ scores, const int *__restrict__ ids, int cols,
+                                                            int k, int idx_offset, float *__restrict__ out_scores,
+                                                            int *__restrict__ out_idx) {
     __shared__ unsigned long long red[kTopkThreads / 32];
     __shared__ unsigned long long chosen;
     const float *row = scores + (size_t)blockIdx.x * cols;
+    const int *row_ids = ids ? ids + (size_t)blockIdx.x * cols : nullptr;
     unsigned long long last = 0ull;
     bool have_last = false;
     for (int it = 0; it < k; it++) {
         unsigned long long m = ~0ull;
+        int mc = -1;
         for (int c = threadIdx.x; c < cols; c += kTopkThreads) {
-            const unsigned long long key = score_key(row[c], c);
-            if ((!have_last || key > last) && key < m) m = key;
+            const int id = row_ids ? row_ids[c] : c;
+            if (id < 0) continue;  // padding entry of a short shard
+            const unsigned long long key = score_key(row[c], id);
+            if ((!have_last || key > last) && key < m) { m = key; mc = c; }
         }
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
-            m = other < m ? other : m;
+            const int oc = __shfl_xor_sync(0xffffffffu, mc, o);
+            if (other < m) { m = other; mc = oc; }
         }
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        __shared__ int red_col[kTopkThreads / 32];
+        if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = m; red_col[threadIdx.x >> 5] = mc; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int i = 1; i < kTopkThreads / 32; i++) m = red[i] < m ? red[i] : m;
+            for (int i = 1; i < kTopkThreads / 32; i++)
+                if (red[i] < m) { m = red[i]; mc = red_col[i]; }
             chosen = m;
-            const int c = (int)(m & 0xffffffffull);
-            out_scores[(size_t)blockIdx.x * k + it] = row[c];
-            out_idx[(size_t)blockIdx.x * k + it] = c + idx_offset;
+            const size_t o = (size_t)blockIdx.x * k + it;
+            if (mc < 0) {  // fewer than k real entries: pad
+                out_scores[o] = kInf;
+                out_idx[o] = -1;
+            } else {
+                out_scores[o] = row[mc];
+                out_idx[o] = (row_ids ? row_ids[mc] : mc) + idx_offset;
+            }
         }
         __syncthreads();
         last = chosen;
@@ -682,7 +698,7 @@ unsigned long long ured_kernel_launches(void) { return g_launches.load(std::memo
 
 size_t ured_packed_bytes(int count, int n) {
     if (count <= 0 || n <= 0) return 256;
-    return align_up((size_t)count * 4 * pad32(n) * sizeof(float), 256) + align_up((size_t)count * sizeof(float), 256);
+    return align_up((size_t)count * cloud_stride(pad32(n)) * sizeof(float), 256);
 }
 
 int ured_pack_clouds(const float *xyz, int count, int n, void *packed, void *stream) {
@@ -690,8 +706,8 @@ int ured_pack_clouds(const float *xyz, int count, int n, void *packed, void *str
     if (count == 0 || n == 0) return 0;
     if (!xyz || !packed) return fail_arg(URED_E_NULL, "ured_pack_clouds: NULL pointer");
     if ((uintptr_t)packed % 256) return fail_arg(URED_E_WORKSPACE, "packed image must be 256-byte aligned");
-    PackedView v = view_packed(packed, count, n);
-    pack_kernel<<<count, kPackThreads, 0, (cudaStream_t)stream>>>(xyz, n, v.np, (float *)v.soa, (float *)v.wmax);
+    PackedView v = view_packed(packed, n);
+    pack_kernel<<<count, kPackThreads, 0, (cudaStream_t)stream>>>(xyz, n, v.np, (float *)v.soa);
     URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "pack_kernel launch");
 }
@@ -717,12 +733,10 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
         return 0;
     }
     if (!xyz1 || !xyz2 || !packed1 || !packed2) return fail_arg(URED_E_NULL, "ured_nn_packed: NULL input");
-    const int cnt1 = count1_of(B, rep1), cnt2 = count2_of(B, mod2);
-    PackedView v1 = view_packed(packed1, cnt1, n1), v2 = view_packed(packed2, cnt2, n2);
+    PackedView v1 = view_packed(packed1, n1), v2 = view_packed(packed2, n2);
     NNParams p;
     p.xyz[0] = xyz1; p.xyz[1] = xyz2;
     p.soa[0] = v1.soa; p.soa[1] = v2.soa;
-    p.wmax[0] = v1.wmax; p.wmax[1] = v2.wmax;
     p.dist[0] = dist1; p.dist[1] = dist2;
     p.idx[0] = idx1; p.idx[1] = idx2;
     p.n[0] = n1; p.n[1] = n2;
@@ -876,9 +890,19 @@ int ured_topk_smallest(const float *scores, int rows, int cols, int k, int idx_o
     if (k > cols || k > 1024) return fail_arg(URED_E_RANGE, "ured_topk_smallest: need k <= cols and k <= 1024");
     if (rows == 0 || k == 0) return 0;
     if (!scores || !out_scores || !out_idx) return fail_arg(URED_E_NULL, "ured_topk_smallest: NULL pointer");
-    topk_kernel<<<rows, kTopkThreads, 0, (cudaStream_t)stream>>>(scores, cols, k, idx_offset, out_scores, out_idx);
+    topk_kernel<<<rows, kTopkThreads, 0, (cudaStream_t)stream>>>(scores, nullptr, cols, k, idx_offset, out_scores, out_idx);
     URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "topk_kernel launch");
+}
+
+int ured_merge_topk(const float *scores, const int *ids, int rows, int cols, int k, float *out_scores, int *out_ids, void *stream) {
+    if (rows < 0 || cols < 0 || k < 0) return fail_arg(URED_E_SHAPE, "negative size");
+    if (k > 1024) return fail_arg(URED_E_RANGE, "ured_merge_topk: k <= 1024");
+    if (rows == 0 || k == 0) return 0;
+    if (!scores || !ids || !out_scores || !out_ids) return fail_arg(URED_E_NULL, "ured_merge_topk: NULL pointer");
+    topk_kernel<<<rows, kTopkThreads, 0, (cudaStream_t)stream>>>(scores, ids, cols, k, 0, out_scores, out_ids);
+    URED_COUNT_LAUNCH();
+    return check_cuda(cudaGetLastError(), "topk_kernel(merge) launch");
 }
 
 }  // extern "C"

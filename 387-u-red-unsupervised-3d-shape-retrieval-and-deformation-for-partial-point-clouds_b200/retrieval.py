@@ -22,7 +22,11 @@ from .dist_chamfer_3D import _require_cloud, _stream
 
 
 class PackedClouds:
-    """[count, n, 3] float32 CUDA clouds plus their resident packed SoA image (TMA source)."""
+    """[count, n, 3] float32 CUDA clouds plus their resident packed SoA image (the TMA source).
+
+    The image is one independent block per cloud (include/ured_chamfer.h), so ``slice(lo, hi)`` is a
+    zero-copy view: a library is packed once and scored slab by slab or shard by shard.
+    """
 
     def __init__(self, xyz):
         if xyz.dim() == 2:
@@ -42,17 +46,30 @@ class PackedClouds:
     def device(self):
         return self.xyz.device
 
+    @property
+    def block_bytes(self):
+        return (4 * ((self.n + 31) // 32 * 32) + 32) * 4
+
+    def slice(self, lo, hi):
+        """Clouds [lo, hi) as a PackedClouds sharing this one's storage."""
+        if not (0 <= lo <= hi <= self.count):
+            raise IndexError(f"slice [{lo}, {hi}) outside [0, {self.count})")
+        view = object.__new__(PackedClouds)
+        view.xyz = self.xyz[lo:hi]
+        view.count, view.n = hi - lo, self.n
+        view.packed = self.packed[lo * self.block_bytes:]
+        return view
+
 
 def _as_packed(c):
     return c if isinstance(c, PackedClouds) else PackedClouds(c)
 
 
-def nn_pairs(cloud1, cloud2, B, rep1, mod2, first2=0, count2=None, exact_only=False):
-    """Nearest neighbours for B pairs: pair b = (cloud1[b // rep1], cloud2[first2 + b % mod2])."""
+def nn_pairs(cloud1, cloud2, B, rep1, mod2, exact_only=False):
+    """Nearest neighbours for B pairs: pair b = (cloud1[b // rep1], cloud2[b % mod2])."""
     lib = _native.load()
     c1, c2 = _as_packed(cloud1), _as_packed(cloud2)
-    count2 = c2.count - first2 if count2 is None else count2
-    if (B + rep1 - 1) // rep1 > c1.count or min(B, mod2) > count2:
+    if (B + rep1 - 1) // rep1 > c1.count or min(B, mod2) > c2.count:
         raise ValueError("pair addressing runs past the clouds provided")
     dev = c1.device
     n1, n2 = c1.n, c2.n
@@ -60,10 +77,6 @@ def nn_pairs(cloud1, cloud2, B, rep1, mod2, first2=0, count2=None, exact_only=Fa
     dist2 = torch.empty(B, n2, device=dev, dtype=torch.float32)
     idx1 = torch.empty(B, n1, device=dev, dtype=torch.int32)
     idx2 = torch.empty(B, n2, device=dev, dtype=torch.int32)
-    # a window [first2, first2+count2) of a packed image: SoA part and max-norm part are offset separately,
-    # so windows are only taken when they start at 0 or the caller packed the shard on its own
-    if first2 != 0:
-        raise ValueError("pack each library shard separately (first2 must be 0)")
     flags = _native.URED_FLAG_EXACT_ONLY if exact_only else 0
     scratch_bytes = lib.ured_nn_scratch_bytes(B, n1, n2)
     scratch = torch.empty(scratch_bytes, device=dev, dtype=torch.uint8) if scratch_bytes else None
@@ -126,7 +139,7 @@ def score_library(targets, library, alpha=1000, n_lambda=1, max_pairs=8192, exac
     q_step = max(1, min(Q, max_pairs // S)) if S <= max_pairs else 1
     for q0 in range(0, Q, q_step):
         q1 = min(Q, q0 + q_step)
-        sub_t = tgts if (q0 == 0 and q1 == Q) else PackedClouds(tgts.xyz[q0:q1])
+        sub_t = tgts.slice(q0, q1)
         if S <= max_pairs:
             raw = nn_pairs(sub_t, lib_c, (q1 - q0) * S, S, S, exact_only=exact_only)
             dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda)
@@ -136,7 +149,7 @@ def score_library(targets, library, alpha=1000, n_lambda=1, max_pairs=8192, exac
         else:  # one target at a time against slabs of the library
             for s0 in range(0, S, max_pairs):
                 s1 = min(S, s0 + max_pairs)
-                slab = PackedClouds(lib_c.xyz[s0:s1])
+                slab = lib_c.slice(s0, s1)
                 raw = nn_pairs(sub_t, slab, s1 - s0, s1 - s0, s1 - s0, exact_only=exact_only)
                 dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda)
                 out[0, q0, s0:s1] = dcd
@@ -183,7 +196,23 @@ def shard_bounds(num_shapes, world_size, rank):
 
 
 def merge_topk(scores, ids, k):
-    """Merge candidate lists [Q, C] by ascending (score, id); ids < 0 mark padding.  Device-agnostic."""
+    """Merge candidate lists [Q, C] by ascending (score, id); ids < 0 mark padding.
+
+    CUDA tensors go through the native kernel (ured_merge_topk); CPU tensors (the gloo-backed tests of the
+    exchange logic) use the equivalent two stable sorts below.
+    """
+    if scores.is_cuda:
+        lib = _native.load()
+        scores = scores.contiguous().float()
+        ids = ids.contiguous().to(torch.int32)
+        Q, C = scores.shape
+        out_s = torch.empty(Q, k, device=scores.device, dtype=torch.float32)
+        out_i = torch.empty(Q, k, device=scores.device, dtype=torch.int32)
+        with torch.cuda.device(scores.device):
+            rc = lib.ured_merge_topk(_native.ptr(scores), _native.ptr(ids), Q, C, k, _native.ptr(out_s), _native.ptr(out_i),
+                                     _stream(scores.device))
+        _native.check(rc, "ured_merge_topk")
+        return out_s, out_i
     scores = torch.where(ids < 0, torch.full_like(scores, float("inf")), scores)
     big = torch.iinfo(ids.dtype).max
     order = torch.sort(torch.where(ids < 0, torch.full_like(ids, big), ids), dim=1, stable=True).indices

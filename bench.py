@@ -30,6 +30,11 @@ METRIC = "Chamfer+DCD fwd+bwd Gpair/s"
 UNIT = "Gpair/s"
 FLOP_PER_PAIR = 8.0  # 3 sub, 3 mul, 2 add: the reference arithmetic
 
+RETRIEVAL = {
+    # name: (library shapes S, queries Q, points, description)   -- sharded over ranks, strong scaling
+    "cfg3": (1000, 1, 2048, "library retrieval: 1 target vs S=1000 shapes x 2048 pts, top-10, library sharded over ranks (BASELINE configs[2])"),
+    "cfg5": (10000, 64, 2048, "retrieval sweep point: 64 targets vs S shapes x 2048 pts, top-10, sharded (BASELINE configs[4]; --library-size)"),
+}
 WORKLOADS = {
     # name: (pairs B, n_x, n_gt, description)
     "cfg2": (640, 2048, 2048, "chair retrieval: 64 targets x K=10 deformed candidates, 2048 pts (BASELINE configs[1])"),
@@ -163,6 +168,101 @@ def run_reference_arm(args, wl):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------
+# sharded library retrieval (cfg3 / cfg5): forward scoring + local top-k + one all_gather + merge
+# ------------------------------------------------------------------------------------------------
+def run_retrieval(args):
+    import torch
+    import torch.distributed as dist
+    import ured_b200 as ured
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    lib = ured._native.load()
+    S, Q, n, desc = RETRIEVAL[args.workload]
+    S = args.library_size or S
+    Q = args.queries or Q
+    k = 10
+    lo, hi = ured.shard_bounds(S, world, rank)
+    # the library shard is generated in slabs (seeded by global shape id range), packed once and kept resident
+    slabs = []
+    for s0 in range(lo, hi, 4096):
+        x, _ = synth(min(4096, hi - s0), n, 8, seed=7000 + s0)
+        slabs.append(x.to(dev))
+    shard = ured.PackedClouds(torch.cat(slabs)) if slabs else None
+    del slabs
+    _, tg_host = synth(Q, 8, n, seed=99)      # same targets on every rank
+    tg_pin = tg_host.pin_memory()
+    tg_dev = tg_pin.to(dev)
+    out_s = torch.empty(Q, k).pin_memory()
+    out_i = torch.empty(Q, k, dtype=torch.int32).pin_memory()
+    pairs_per_step = 2.0 * Q * S * n * n
+
+    def step_device():
+        return ured.retrieve_sharded(tg_dev, shard, lo, k=k, metric="cd_t")
+
+    def step_e2e():
+        t = tg_pin.to(dev, non_blocking=True)
+        v, i = ured.retrieve_sharded(t, shard, lo, k=k, metric="cd_t")
+        out_s.copy_(v, non_blocking=True)
+        out_i.copy_(i, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if sampler:
+            sampler.start()
+        l0 = lib.ured_kernel_launches()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        launches = lib.ured_kernel_launches() - l0
+        if sampler:
+            sampler.stop()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, launches
+
+    sampler = ClockSampler(local_rank)
+    ms_step, launches = timed(step_device, args.steps, args.warmup, sampler)
+    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    v, i = step_device()
+    torch.cuda.synchronize()
+    line = {
+        "metric": "Chamfer+DCD fwd Gpair/s (sharded retrieval, top-k merged)", "value": pairs_per_step / (ms_step * 1e-3) / 1e9, "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "library_shapes": S, "queries": Q, "points": n, "top_k": k,
+                   "shard": [lo, hi], "collective": "one all_gather of [Q,k] (score,id) pairs per step" if world > 1 else "none (1 rank)",
+                   "l2": "library shard (%.0f MB packed + raw) exceeds L2 except at the smallest sizes" % ((hi - lo) * n * 28 / 1e6)},
+        "e2e": {"value": pairs_per_step / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(tg_pin.numel() * 4), "d2h_bytes_per_step": int(Q * k * 8)},
+        "gpu_launches": int(launches), "clocks": sampler.summary(),
+        "top1": {"score": float(v[0, 0]), "id": int(i[0, 0])},
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -172,14 +272,19 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + sorted(RETRIEVAL))
+    ap.add_argument("--library-size", type=int, default=0, help="override S for the retrieval workloads")
+    ap.add_argument("--queries", type=int, default=0, help="override Q for the retrieval workloads")
     ap.add_argument("--exact-only", action="store_true", help="disable the screening pass (difference form on every pair)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
-        run_reference_arm(args, args.workload)
+        run_reference_arm(args, args.workload if args.workload in WORKLOADS else "cfg2")
+        return
+    if args.workload in RETRIEVAL:
+        run_retrieval(args)
         return
 
     import torch

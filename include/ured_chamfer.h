@@ -67,10 +67,12 @@ unsigned long long ured_kernel_launches(void);
 
 /* ---- packed clouds ---------------------------------------------------------------------
  * The nearest-neighbour kernel stages the opposing cloud through shared memory with TMA bulk
- * copies from a packed, padded structure-of-arrays image: per cloud X[np] | Y[np] | Z[np] |
- * W[np] with np = n rounded up to 32, W = x^2+y^2+z^2, padding = copies of the last point;
- * followed (at the end of the whole image) by one float per cloud holding max W.
- * A library that is scored against many targets is packed once and kept resident. */
+ * copies from a packed, padded structure-of-arrays image: per cloud one block
+ *     X[np] | Y[np] | Z[np] | W[np] | tail[32]      (floats; np = n rounded up to 32)
+ * with W = x^2+y^2+z^2, padding = copies of the last point, tail[0] = max W of the cloud.
+ * Blocks are independent: a pointer to block i is a valid packed image of clouds i, i+1, ...
+ * (block stride = ured_packed_bytes(1, n) rounded down to (4*np + 32) * 4 bytes), so a library that
+ * is scored against many targets is packed once, kept resident, and addressed by slices. */
 size_t ured_packed_bytes(int count, int n);
 int ured_pack_clouds(const float *xyz, int count, int n, void *packed, void *stream);
 
@@ -143,6 +145,12 @@ int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n
  * of a library shard).  k <= cols is required; k <= 1024. */
 int ured_topk_smallest(const float *scores, int rows, int cols, int k, int idx_offset,
                        float *out_scores, int *out_idx, void *stream);
+
+/* Merge step of sharded retrieval: rows of `cols` candidates (score, id) gathered from all shards -> the k
+ * smallest in ascending (score, id) order.  ids must be unique per row; ids < 0 mark padding; if a row holds
+ * fewer than k real entries the tail is (+inf, -1). */
+int ured_merge_topk(const float *scores, const int *ids, int rows, int cols, int k,
+                    float *out_scores, int *out_ids, void *stream);
 
 #ifdef __cplusplus
 }

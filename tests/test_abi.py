@@ -30,9 +30,9 @@ def test_header_symbols_are_exported(ured):
 def test_abi_version_and_sizes(ured):
     lib = ured._native.load()
     assert lib.ured_abi_version() == 1
-    # 2 clouds of 2048 points: 2 * 4 arrays * 2048 floats, plus one max-norm float per cloud, 256-aligned
-    assert lib.ured_packed_bytes(2, 2048) == 2 * 4 * 2048 * 4 + 256
-    assert lib.ured_packed_bytes(1, 100) == 4 * 128 * 4 + 256  # padded to 32 points
+    # per cloud: 4 arrays of np floats + a 32-float tail holding the max norm; 256-aligned in total
+    assert lib.ured_packed_bytes(2, 2048) == 2 * (4 * 2048 + 32) * 4
+    assert lib.ured_packed_bytes(1, 100) == (4 * 128 + 32) * 4 + 128  # padded to 32 points, rounded up to 256 bytes
     assert lib.ured_chamfer_workspace_bytes(3, 100, 200) == lib.ured_packed_bytes(3, 100) + lib.ured_packed_bytes(3, 200) + lib.ured_nn_scratch_bytes(3, 100, 200)
     assert lib.ured_nn_scratch_bytes(640, 2048, 2048) == 0            # enough pairs: no candidate splitting
     assert lib.ured_nn_scratch_bytes(16, 16384, 16384) == 4 * 16 * 32768 * 8  # dense clouds: 4 splits of partial (d, idx)
