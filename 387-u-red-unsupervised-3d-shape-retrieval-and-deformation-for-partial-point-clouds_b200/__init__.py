@@ -13,14 +13,14 @@ from . import _native
 from ._native import NativeLibraryError, build_native
 from .dist_chamfer_3D import chamfer_3DDist, chamfer_3DFunction, nn_forward, nn_backward
 from .dist_chamfer_3D import chamfer_3DDist as cd
-from .model_utils import calc_cd, calc_dcd, fscore
+from .model_utils import calc_cd, calc_dcd, chamfer_ragged, fscore
 from .chamfer_loss import ChamferLoss, chamfer_distance2, compute_cm_loss
 from . import retrieval
 from .retrieval import (PackedClouds, score_candidates, score_library, topk_smallest, retrieve,
                         retrieve_sharded, shard_bounds, merge_topk, gather_and_merge)
 
 __all__ = [
-    "chamfer_3DDist", "chamfer_3DFunction", "nn_forward", "nn_backward", "cd", "fscore", "calc_cd", "calc_dcd",
+    "chamfer_3DDist", "chamfer_3DFunction", "nn_forward", "nn_backward", "cd", "fscore", "calc_cd", "calc_dcd", "chamfer_ragged",
     "ChamferLoss", "chamfer_distance2", "compute_cm_loss",
     "PackedClouds", "score_candidates", "score_library", "topk_smallest", "retrieve",
     "retrieve_sharded", "shard_bounds", "merge_topk", "gather_and_merge",

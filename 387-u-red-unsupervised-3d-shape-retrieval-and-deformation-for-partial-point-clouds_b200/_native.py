@@ -22,46 +22,25 @@ NVCC_FLAGS = [
 ]
 
 URED_FLAG_EXACT_ONLY = 1
+URED_FLAG_NON_REG = 2
 
-_c_float_p = ctypes.c_void_p  # device pointers travel as integers
+_i, _u, _f, _p, _sz = ctypes.c_int, ctypes.c_uint, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 _SIGNATURES = {
-    # name: (restype, argtypes)
-    "ured_abi_version": (ctypes.c_int, []),
+    # name: (restype, argtypes) -- device pointers travel as integers (c_void_p)
+    "ured_abi_version": (_i, []),
     "ured_last_error_string": (ctypes.c_char_p, []),
     "ured_kernel_launches": (ctypes.c_ulonglong, []),
-    "ured_packed_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
-    "ured_pack_clouds": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
-    "ured_nn_scratch_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
-    "ured_nn_packed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
-                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
-                                      ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                      ctypes.c_void_p, ctypes.c_size_t,
-                                      ctypes.c_uint, ctypes.c_void_p]),
-    "ured_chamfer_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
-    "ured_chamfer_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint, ctypes.c_void_p]),
-    "ured_chamfer_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                             ctypes.c_int, ctypes.c_int,
-                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
-    "ured_dcd_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                        ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                        ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
-                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
-    "ured_dcd_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                         ctypes.c_int, ctypes.c_int,
-                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float,
-                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                         ctypes.c_void_p, ctypes.c_void_p,
-                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
-    "ured_merge_topk": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
-    "ured_topk_smallest": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "ured_packed_bytes": (_sz, [_i, _i]),
+    "ured_pack_clouds": (_i, [_p, _i, _i, _p, _p, _p]),
+    "ured_nn_scratch_bytes": (_sz, [_i, _i, _i]),
+    "ured_nn_packed": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _u, _p]),
+    "ured_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ured_chamfer_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _u, _p]),
+    "ured_chamfer_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ured_dcd_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _f, _f, _f, _f, _u, _p, _p, _p, _p, _p, _p]),
+    "ured_dcd_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ured_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "ured_topk_smallest": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -29,20 +29,43 @@ def chamfer_distance2(p1, p2):
 
 
 def compute_cm_loss(source_p, target_p, target_part, mask=None, batch_reduction="mean"):
-    """loss/chamfer_loss.py:13-30 -- full-shape and per-part Chamfer of deformed sources.
+    """loss/chamfer_loss.py:13-30 -- full-shape and per-part Chamfer of deformed sources, as TWO batched calls.
 
-    With ``mask`` ([B, parts]) sample ``bs`` uses its first ``mask[bs].sum() * 1024`` source points
-    against the 2048-point target, and part ``i`` uses source points [i*1024, (i+1)*1024) against
-    the ragged ``target_part[bs][i]``.  Returns (mean full loss, mean part loss).  Without a mask
-    it is ``chamfer_distance2(source_p, target_p)``.
+    With ``mask`` ([B, parts]) sample ``bs`` uses its first ``mask[bs].sum() * 1024`` source points against the
+    2048-point target, and part ``i`` uses source points [i*1024, (i+1)*1024) against the ragged
+    ``target_part[bs][i]``.  Returns (mean full loss, mean part loss).  Without a mask it is
+    ``chamfer_distance2(source_p, target_p)``.
+
+    The reference loops over samples and parts in Python with one ``.item()`` sync and one B=1 Chamfer call per
+    sample and per part; here the source lengths stay on the device and both the full-shape and the per-part
+    losses are one ragged batched call each (``chamfer_ragged``).
     """
     if mask is None:
         return chamfer_distance2(source_p, target_p)
-    counts = (mask.sum(1) * 1024).tolist()  # one host sync for the batch (the reference syncs per sample)
-    loss_all, loss_part = [], []
-    for bs in range(len(source_p)):
-        loss_all.append(chamfer_distance2(source_p[bs:bs + 1, :int(counts[bs])], target_p[bs:bs + 1]))
-        parts = [chamfer_distance2(source_p[bs:bs + 1, i * 1024:(i + 1) * 1024], target_part[bs][i].unsqueeze(0))
-                 for i in range(len(target_part[bs]))]
-        loss_part.append(torch.stack(parts).mean())
-    return torch.stack(loss_all).mean(), torch.stack(loss_part).mean()
+    from .model_utils import chamfer_ragged
+    B = source_p.shape[0]
+    dev = source_p.device
+    src = source_p.float()
+    # ---- full shapes: x = source (ragged length), gt = target ---------------------------------
+    len_src = (mask.sum(1) * 1024).to(torch.int32)
+    _, _, full, _, _, _, _ = chamfer_ragged(src, target_p.float(), len_x=len_src, alpha=0.0)
+    # ---- parts: one pair per (sample, part) present in target_part ----------------------------
+    n_parts = [len(tp) for tp in target_part]
+    P = max(n_parts) if n_parts else 0
+    if P == 0:
+        return full.mean(), full.new_zeros(())
+    if src.shape[1] < P * 1024:
+        raise ValueError("source_p has fewer than 1024 points per target part")
+    m_max = max(t.shape[0] for tp in target_part for t in tp)
+    tgt = src.new_zeros(B * P, m_max, 3)
+    len_tgt = torch.zeros(B * P, dtype=torch.int32)
+    for bs, tp in enumerate(target_part):
+        for i, t in enumerate(tp):
+            tgt[bs * P + i, :t.shape[0]] = t
+            len_tgt[bs * P + i] = t.shape[0]
+    len_tgt = len_tgt.to(dev)
+    parts_src = src[:, :P * 1024].reshape(B * P, 1024, 3)
+    _, _, per_part, _, _, _, _ = chamfer_ragged(parts_src, tgt, len_gt=len_tgt, alpha=0.0)
+    present = (len_tgt > 0).view(B, P).to(per_part.dtype)
+    loss_part = (per_part.view(B, P) * present).sum(1) / present.sum(1)
+    return full.mean(), loss_part.mean()

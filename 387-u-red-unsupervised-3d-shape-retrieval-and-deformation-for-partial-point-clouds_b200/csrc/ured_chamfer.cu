@@ -72,10 +72,12 @@ constexpr int kPackTail = 32;  // floats after X|Y|Z|W of each cloud: [0] = max 
 inline size_t cloud_stride(int np) { return (size_t)np * 4 + kPackTail; }
 
 // one CTA per cloud; writes the cloud's block X|Y|Z|W (each np floats) | tail (max W)
-__global__ void __launch_bounds__(kPackThreads) pack_kernel(const float *__restrict__ xyz, int n, int np,
-                                                            float *__restrict__ soa) {
+// len (optional): number of valid points of each cloud (ragged batches); everything past it replicates the last valid point
+__global__ void __launch_bounds__(kPackThreads) pack_kernel(const float *__restrict__ xyz, int n_max, int np,
+                                                            float *__restrict__ soa, const int *__restrict__ len) {
     const size_t cloud = blockIdx.x;
-    const float *src = xyz + cloud * (size_t)n * 3;
+    const int n = len ? max(1, min(len[cloud], n_max)) : n_max;  // (an empty cloud is never read as candidates)
+    const float *src = xyz + cloud * (size_t)n_max * 3;
     float *X = soa + cloud * ((size_t)np * 4 + kPackTail);
     float *Y = X + np, *Z = Y + np, *W = Z + np;
     float *wmax = W + np;
@@ -168,6 +170,7 @@ struct NNParams {
     int B;
     float *part_dist[2];
     int *part_idx[2];
+    const int *len[2];  // optional valid point counts per cloud-1 / cloud-2 entry (ragged batches)
 };
 
 // the reference's pair arithmetic (chamfer3D.cu:32-35 as compiled by nvcc 12.9 for sm_100a):
@@ -196,9 +199,28 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
     const int c1 = b / p.rep1, c2 = b % p.mod2;
     const int cq = dir ? c2 : c1, cc = dir ? c1 : c2;
     // (ternaries, not p.x[dir]: dynamic indexing would copy the parameter block to local memory)
-    const int nq = dir ? p.n[1] : p.n[0], nc = dir ? p.n[0] : p.n[1], ncp = dir ? p.np[0] : p.np[1];
+    const int nq = dir ? p.n[1] : p.n[0];                                  // row stride of the outputs (max points)
+    const int ncp_max = dir ? p.np[0] : p.np[1];                             // padded stride of the candidate image
+    const int *len_q = dir ? p.len[1] : p.len[0], *len_c = dir ? p.len[0] : p.len[1];
+    const int nq_v = len_q ? max(0, min(len_q[cq], nq)) : nq;              // valid queries of this cloud
+    const int nc = len_c ? max(0, min(len_c[cc], dir ? p.n[0] : p.n[1])) : (dir ? p.n[0] : p.n[1]);  // valid candidates
+    const int ncp = (nc + kChunk - 1) / kChunk * kChunk;
     const float *__restrict__ qxyz = (dir ? p.xyz[1] : p.xyz[0]) + (size_t)cq * nq * 3;
-    const float *__restrict__ csoa = (dir ? p.soa[0] : p.soa[1]) + (size_t)cc * ((size_t)ncp * 4 + kPackTail);
+    const float *__restrict__ csoa = (dir ? p.soa[0] : p.soa[1]) + (size_t)cc * ((size_t)ncp_max * 4 + kPackTail);
+
+    float *out_d = p.nsplit == 1 ? (dir ? p.dist[1] : p.dist[0]) + (size_t)b * nq
+                                 : (dir ? p.part_dist[1] : p.part_dist[0]) + ((size_t)sp * p.B + b) * nq;
+    int *out_i = p.nsplit == 1 ? (dir ? p.idx[1] : p.idx[0]) + (size_t)b * nq
+                               : (dir ? p.part_idx[1] : p.part_idx[0]) + ((size_t)sp * p.B + b) * nq;
+    if (qt * R * kNNThreads >= nq_v || nc == 0) {
+        // nothing to search: the reference kernel leaves its zero-filled outputs untouched in this case
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int j = (qt * R + r) * kNNThreads + tid;
+            if (j < nq) { out_d[j] = 0.0f; out_i[j] = 0; }
+        }
+        return;
+    }
 
     // candidate range of this split, in whole 32-candidate chunks
     const int chunks_per_split = (ncp / kChunk + p.nsplit - 1) / p.nsplit;
@@ -215,7 +237,7 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
         mbar_arrive_expect_tx(&full_bar[s], bytes * NARR);
 #pragma unroll
         for (int a = 0; a < NARR; a++)
-            tma_bulk_g2s(stage_mem + (s * NARR + a) * kTile, csoa + (size_t)a * ncp + k0, bytes, &full_bar[s]);
+            tma_bulk_g2s(stage_mem + (s * NARR + a) * kTile, csoa + (size_t)a * ncp_max + k0, bytes, &full_bar[s]);
     };
     if (tid == 0) {
 #pragma unroll
@@ -238,7 +260,7 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
 #pragma unroll
     for (int r = 0; r < R; r++) {
         int j = (qt * R + r) * kNNThreads + tid;
-        j = j < nq ? j : nq - 1;
+        j = j < nq_v ? j : nq_v - 1;
         qx[r] = kScale * qxyz[j * 3 + 0]; qy[r] = kScale * qxyz[j * 3 + 1]; qz[r] = kScale * qxyz[j * 3 + 2];
         best[r] = kInf; second[r] = kInf; bchunk[r] = k_lo;
     }
@@ -311,9 +333,9 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
     }
 
     // ---- exact resolution of the winning chunk ---------------------------------------------
-    const float *__restrict__ gX = csoa, *__restrict__ gY = csoa + ncp, *__restrict__ gZ = csoa + 2 * (size_t)ncp;
+    const float *__restrict__ gX = csoa, *__restrict__ gY = csoa + ncp_max, *__restrict__ gZ = csoa + 2 * (size_t)ncp_max;
     float cn = 0.0f;
-    if (SCREEN) cn = __fsqrt_ru(csoa[(size_t)ncp * 4]) * 1.000001f;  // max W of the candidate cloud (block tail)
+    if (SCREEN) cn = __fsqrt_ru(csoa[(size_t)ncp_max * 4]) * 1.000001f;  // max W of the candidate cloud (block tail)
     const int lane = tid & 31;
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -365,15 +387,10 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
         }
         const int j = (qt * R + r) * kNNThreads + tid;
         if (j < nq) {
-            if (p.nsplit == 1) {
-                (dir ? p.dist[1] : p.dist[0])[(size_t)b * nq + j] = bd;
-                (dir ? p.idx[1] : p.idx[0])[(size_t)b * nq + j] = bi;
-            } else {
-                if (k_lo >= k_hi) bd = kInf;  // empty split
-                const size_t o = ((size_t)sp * p.B + b) * nq + j;
-                (dir ? p.part_dist[1] : p.part_dist[0])[o] = bd;
-                (dir ? p.part_idx[1] : p.part_idx[0])[o] = bi;
-            }
+            if (j >= nq_v) { bd = 0.0f; bi = 0; }                          // past the valid length of a ragged cloud
+            else if (p.nsplit > 1 && k_lo >= k_hi) bd = kInf;              // empty split: loses every merge
+            out_d[j] = bd;
+            out_i[j] = bi;
         }
     }
 }
@@ -430,19 +447,40 @@ __device__ __forceinline__ float pow_lambda(float c, float n_lambda) {
 }
 
 // one CTA per pair: shared-memory histograms of idx1 (bins = points of cloud 2) and idx2
+// len1/len2 (optional): valid point counts per cloud entry; pair b uses len1[b / rep1], len2[b % mod2].  With lengths the
+// means run over the valid points only and the DCD fractions are rebuilt from them (non_reg clamps them at 1).
+struct DcdLens { const int *len1, *len2; int rep1, mod2, non_reg; };
+
 __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__restrict__ dist1, const float *__restrict__ dist2,
                                                               const int *__restrict__ idx1, const int *__restrict__ idx2,
-                                                              int n1, int n2, float alpha, float n_lambda, float frac_12,
+                                                              int n1_max, int n2_max, float alpha, float n_lambda, float frac_12,
                                                               float frac_21, float *__restrict__ loss, float *__restrict__ cd_p,
                                                               float *__restrict__ cd_t, float *__restrict__ ew1,
-                                                              float *__restrict__ ew2) {
+                                                              float *__restrict__ ew2, const DcdLens lens) {
     extern __shared__ int hist[];  // count1[n2] | count2[n1]
     __shared__ double red[(kDcdThreads / 32) * 6];
-    int *count1 = hist, *count2 = hist + n2;
+    int *count1 = hist, *count2 = hist + n2_max;
     const size_t b = blockIdx.x;
-    const float *d1 = dist1 + b * n1, *d2 = dist2 + b * n2;
-    const int *i1 = idx1 + b * n1, *i2 = idx2 + b * n2;
-    for (int k = threadIdx.x; k < n1 + n2; k += kDcdThreads) hist[k] = 0;
+    const float *d1 = dist1 + b * n1_max, *d2 = dist2 + b * n2_max;
+    const int *i1 = idx1 + b * n1_max, *i2 = idx2 + b * n2_max;
+    const int n1 = lens.len1 ? max(0, min(lens.len1[b / lens.rep1], n1_max)) : n1_max;
+    const int n2 = lens.len2 ? max(0, min(lens.len2[b % lens.mod2], n2_max)) : n2_max;
+    if (lens.len1 || lens.len2) {
+        frac_12 = (float)((double)n2 / (double)max(n1, 1));
+        frac_21 = (float)((double)n1 / (double)max(n2, 1));
+        if (lens.non_reg) { frac_12 = fmaxf(frac_12, 1.0f); frac_21 = fmaxf(frac_21, 1.0f); }
+    }
+    if (n1 == 0 || n2 == 0) {  // an empty side: nothing to average (callers mask such pairs out)
+        for (int k = threadIdx.x; k < n1_max; k += kDcdThreads) if (ew1) ew1[b * n1_max + k] = 0.0f;
+        for (int k = threadIdx.x; k < n2_max; k += kDcdThreads) if (ew2) ew2[b * n2_max + k] = 0.0f;
+        if (threadIdx.x == 0) {
+            if (loss) loss[b] = 0.0f;
+            if (cd_p) cd_p[b] = 0.0f;
+            if (cd_t) cd_t[b] = 0.0f;
+        }
+        return;
+    }
+    for (int k = threadIdx.x; k < n1_max + n2_max; k += kDcdThreads) hist[k] = 0;
     __syncthreads();
     for (int k = threadIdx.x; k < n1; k += kDcdThreads) atomicAdd(&count1[i1[k]], 1);
     for (int k = threadIdx.x; k < n2; k += kDcdThreads) atomicAdd(&count2[i2[k]], 1);
@@ -454,12 +492,14 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
 #pragma unroll
     for (int side = 0; side < 2; side++) {
         const int n = side ? n2 : n1;
+        const int n_stride = side ? n2_max : n1_max;
         const float *d = side ? d2 : d1;
         const int *ix = side ? i2 : i1;
         const int *cnt = side ? count2 : count1;
         const float frac = side ? frac_12 : frac_21;
         float *ew = side ? ew2 : ew1;
         double a_term = 0.0, a_d = 0.0, a_sqrt = 0.0;
+        if (ew) for (int k = n + threadIdx.x; k < n_stride; k += kDcdThreads) ew[b * n_stride + k] = 0.0f;
         for (int k = threadIdx.x; k < n; k += kDcdThreads) {
             const float dk = d[k];
             const float c = (float)cnt[ix[k]];
@@ -467,7 +507,7 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
             const float e = expf(__fmul_rn(-dk, alpha));
             const float w = __fmul_rn(__fdiv_rn(1.0f, __fadd_rn(pow_lambda(c, n_lambda), 1e-6f)), frac);
             const float ewk = __fmul_rn(e, w);
-            if (ew) ew[b * n + k] = ewk;
+            if (ew) ew[b * n_stride + k] = ewk;
             a_term += (double)__fsub_rn(1.0f, ewk);
             a_d += (double)dk;
             a_sqrt += (double)sqrtf(dk);
@@ -516,7 +556,11 @@ struct GradParams {
     int n[2];
     int rep1, mod2;
     float alpha;
+    const int *len[2];  // optional valid point counts per cloud-1 / cloud-2 entry
 };
+__device__ __forceinline__ int valid_len(const int *len, size_t cloud, int n_max) {
+    return len ? max(0, min(len[cloud], n_max)) : n_max;
+}
 
 __device__ __forceinline__ float point_grad_coeff(const GradParams &p, int side, size_t b, size_t pt, int n_own);
 
@@ -534,8 +578,17 @@ __global__ void __launch_bounds__(kGradThreads) grad_kernel(const GradParams p) 
         const size_t c1 = b / p.rep1, c2 = b % p.mod2;
         const size_t c_own = side ? c2 : c1, c_oth = side ? c1 : c2;
         const size_t pt = b * n_own + j;
+        const int v_own = valid_len(side ? p.len[1] : p.len[0], c_own, n_own);
+        const int v_oth = valid_len(side ? p.len[0] : p.len[1], c_oth, n_oth);
+        if (j >= v_own || v_oth == 0) {  // past the valid length (or nothing to match): zero gradient
+            if (PHASE == 0 && !(side ? SHARED2 : SHARED1)) {
+                float *dst = (side ? p.grad[1] : p.grad[0]) + (c_own * n_own + j) * 3;
+                dst[0] = 0.0f; dst[1] = 0.0f; dst[2] = 0.0f;
+            }
+            continue;
+        }
         // upstream gradient w.r.t. this point's squared NN distance
-        const float gd = point_grad_coeff(p, side, b, pt, n_own);
+        const float gd = point_grad_coeff(p, side, b, pt, v_own);
         const int j2 = (side ? p.idx[1] : p.idx[0])[pt];
         const float *a = (side ? p.xyz[1] : p.xyz[0]) + (c_own * n_own + j) * 3;
         const float *o = (side ? p.xyz[0] : p.xyz[1]) + (c_oth * n_oth + j2) * 3;
@@ -585,7 +638,10 @@ __global__ void __launch_bounds__(kGradSmemThreads) grad_smem_kernel(const GradP
         const int j = side ? t - n1 : t;
         const int n_own = side ? n2 : n1;
         const size_t pt = b * n_own + j;
-        const float gd = point_grad_coeff(p, side, b, pt, n_own);
+        const int v_own = valid_len(side ? p.len[1] : p.len[0], b, n_own);
+        const int v_oth = valid_len(side ? p.len[0] : p.len[1], b, side ? n1 : n2);
+        if (j >= v_own || v_oth == 0) continue;
+        const float gd = point_grad_coeff(p, side, b, pt, v_own);
         const int j2 = (side ? p.idx[1] : p.idx[0])[pt];
         const float *a = (side ? xyz2 : xyz1) + j * 3;
         const float *o = (side ? xyz1 : xyz2) + j2 * 3;
@@ -701,13 +757,13 @@ size_t ured_packed_bytes(int count, int n) {
     return align_up((size_t)count * cloud_stride(pad32(n)) * sizeof(float), 256);
 }
 
-int ured_pack_clouds(const float *xyz, int count, int n, void *packed, void *stream) {
+int ured_pack_clouds(const float *xyz, int count, int n, const int *len, void *packed, void *stream) {
     if (count < 0 || n < 0) return fail_arg(URED_E_SHAPE, "negative size");
     if (count == 0 || n == 0) return 0;
     if (!xyz || !packed) return fail_arg(URED_E_NULL, "ured_pack_clouds: NULL pointer");
     if ((uintptr_t)packed % 256) return fail_arg(URED_E_WORKSPACE, "packed image must be 256-byte aligned");
     PackedView v = view_packed(packed, n);
-    pack_kernel<<<count, kPackThreads, 0, (cudaStream_t)stream>>>(xyz, n, v.np, (float *)v.soa);
+    pack_kernel<<<count, kPackThreads, 0, (cudaStream_t)stream>>>(xyz, n, v.np, (float *)v.soa, len);
     URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "pack_kernel launch");
 }
@@ -719,8 +775,8 @@ size_t ured_nn_scratch_bytes(int B, int n1, int n2) {
 }
 
 int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *xyz2, const void *packed2, int n2, int B,
-                   int rep1, int mod2, float *dist1, float *dist2, int *idx1, int *idx2, void *scratch, size_t scratch_bytes,
-                   unsigned flags, void *stream) {
+                   int rep1, int mod2, const int *len1, const int *len2, float *dist1, float *dist2, int *idx1, int *idx2,
+                   void *scratch, size_t scratch_bytes, unsigned flags, void *stream) {
     int rc = check_pairs(B, n1, n2, rep1, mod2);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -742,6 +798,7 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
     p.n[0] = n1; p.n[1] = n2;
     p.np[0] = v1.np; p.np[1] = v2.np;
     p.rep1 = rep1; p.mod2 = mod2;
+    p.len[0] = len1; p.len[1] = len2;
     const bool exact = (flags & URED_FLAG_EXACT_ONLY) != 0;
     const NNShape sh = choose_nn_shape(B, n1, n2);
     const int R = sh.R;
@@ -778,8 +835,9 @@ size_t ured_chamfer_workspace_bytes(int B, int n1, int n2) {
     return ured_packed_bytes(B, n1) + ured_packed_bytes(B, n2) + ured_nn_scratch_bytes(B, n1, n2);
 }
 
-int ured_chamfer_forward(const float *xyz1, const float *xyz2, int B, int n1, int n2, float *dist1, float *dist2, int *idx1,
-                         int *idx2, void *workspace, size_t workspace_bytes, unsigned flags, void *stream) {
+int ured_chamfer_forward(const float *xyz1, const float *xyz2, int B, int n1, int n2, const int *len1, const int *len2,
+                         float *dist1, float *dist2, int *idx1, int *idx2, void *workspace, size_t workspace_bytes,
+                         unsigned flags, void *stream) {
     int rc = check_pairs(B, n1, n2, 1, B > 0 ? B : 1);
     if (rc) return rc;
     if (B == 0) return 0;
@@ -792,20 +850,21 @@ int ured_chamfer_forward(const float *xyz1, const float *xyz2, int B, int n1, in
     void *pk1 = workspace;
     void *pk2 = (char *)workspace + ured_packed_bytes(B, n1);
     if (n1 > 0 && n2 > 0) {
-        rc = ured_pack_clouds(xyz1, B, n1, pk1, stream);
+        rc = ured_pack_clouds(xyz1, B, n1, len1, pk1, stream);
         if (rc) return rc;
-        rc = ured_pack_clouds(xyz2, B, n2, pk2, stream);
+        rc = ured_pack_clouds(xyz2, B, n2, len2, pk2, stream);
         if (rc) return rc;
     }
     void *scratch = (char *)pk2 + ured_packed_bytes(B, n2);
-    return ured_nn_packed(xyz1, pk1, n1, xyz2, pk2, n2, B, 1, B, dist1, dist2, idx1, idx2, scratch,
+    return ured_nn_packed(xyz1, pk1, n1, xyz2, pk2, n2, B, 1, B, len1, len2, dist1, dist2, idx1, idx2, scratch,
                           ured_nn_scratch_bytes(B, n1, n2), flags, stream);
 }
 
 int ured_dcd_forward(const float *dist1, const float *dist2, const int *idx1, const int *idx2, int B, int n1, int n2,
-                     float alpha, float n_lambda, float frac_12, float frac_21, float *loss, float *cd_p, float *cd_t,
-                     float *ew1, float *ew2, void *stream) {
+                     int rep1, int mod2, const int *len1, const int *len2, float alpha, float n_lambda, float frac_12,
+                     float frac_21, unsigned flags, float *loss, float *cd_p, float *cd_t, float *ew1, float *ew2, void *stream) {
     if (B < 0 || n1 < 0 || n2 < 0) return fail_arg(URED_E_SHAPE, "negative size");
+    if (rep1 < 1 || mod2 < 1) return fail_arg(URED_E_SHAPE, "rep1 and mod2 must be >= 1");
     if (B == 0) return 0;
     if (n1 == 0 || n2 == 0) return fail_arg(URED_E_SHAPE, "ured_dcd_forward: empty cloud");
     if (!dist1 || !dist2 || !idx1 || !idx2) return fail_arg(URED_E_NULL, "ured_dcd_forward: NULL input");
@@ -816,13 +875,16 @@ int ured_dcd_forward(const float *dist1, const float *dist2, const int *idx1, co
         URED_CUDA(cudaFuncSetAttribute(dcd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "dcd smem attribute");
         attr_done = true;
     }
+    DcdLens lens;
+    lens.len1 = len1; lens.len2 = len2; lens.rep1 = rep1; lens.mod2 = mod2; lens.non_reg = (flags & URED_FLAG_NON_REG) ? 1 : 0;
     dcd_fwd_kernel<<<B, kDcdThreads, smem, (cudaStream_t)stream>>>(dist1, dist2, idx1, idx2, n1, n2, alpha, n_lambda, frac_12,
-                                                                   frac_21, loss, cd_p, cd_t, ew1, ew2);
+                                                                   frac_21, loss, cd_p, cd_t, ew1, ew2, lens);
     URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "dcd_fwd_kernel launch");
 }
 
-int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n2, int rep1, int mod2, const float *dist1,
+int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n2, int rep1, int mod2, const int *len1,
+                      const int *len2, const float *dist1,
                       const float *dist2, const int *idx1, const int *idx2, const float *ew1, const float *ew2, float alpha,
                       const float *g_loss, const float *g_cd_p, const float *g_cd_t, const float *g_dist1,
                       const float *g_dist2, float *gradxyz1, float *gradxyz2, void *stream) {
@@ -851,6 +913,7 @@ int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n
     p.n[0] = n1; p.n[1] = n2;
     p.rep1 = rep1; p.mod2 = mod2;
     p.alpha = alpha;
+    p.len[0] = len1; p.len[1] = len2;
     const size_t smem_need = (size_t)(n1 + n2) * 3 * sizeof(float);
     if (!shared1 && !shared2 && smem_need <= 96 * 1024) {
         static thread_local bool attr_done = false;
@@ -877,10 +940,10 @@ int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n
     return check_cuda(cudaGetLastError(), "grad_kernel<scatter> launch");
 }
 
-int ured_chamfer_backward(const float *xyz1, const float *xyz2, int B, int n1, int n2, int rep1, int mod2,
-                          const float *graddist1, const float *graddist2, const int *idx1, const int *idx2, float *gradxyz1,
-                          float *gradxyz2, void *stream) {
-    return ured_dcd_backward(xyz1, xyz2, B, n1, n2, rep1, mod2, nullptr, nullptr, idx1, idx2, nullptr, nullptr, 0.0f, nullptr,
+int ured_chamfer_backward(const float *xyz1, const float *xyz2, int B, int n1, int n2, int rep1, int mod2, const int *len1,
+                          const int *len2, const float *graddist1, const float *graddist2, const int *idx1, const int *idx2,
+                          float *gradxyz1, float *gradxyz2, void *stream) {
+    return ured_dcd_backward(xyz1, xyz2, B, n1, n2, rep1, mod2, len1, len2, nullptr, nullptr, idx1, idx2, nullptr, nullptr, 0.0f, nullptr,
                              nullptr, nullptr, graddist1, graddist2, gradxyz1, gradxyz2, stream);
 }
 

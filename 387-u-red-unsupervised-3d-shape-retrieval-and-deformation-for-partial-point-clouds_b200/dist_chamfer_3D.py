@@ -34,8 +34,20 @@ def _stream(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def nn_forward(xyz1, xyz2, exact_only=None):
+def _len_arg(name, t, count, device):
+    """Validate an optional per-cloud length tensor (ragged batches): int32 [count] on the clouds' device."""
+    if t is None:
+        return None
+    if t.numel() != count:
+        raise ValueError(f"{name} must have one entry per cloud ({count}), got {t.numel()}")
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
+def nn_forward(xyz1, xyz2, exact_only=None, len1=None, len2=None):
     """Raw forward: (dist1, dist2, idx1, idx2) for contiguous float32 CUDA clouds.
+
+    ``len1`` / ``len2`` (optional int tensors [B], may live on the device) give the number of valid points of
+    each cloud; rows are padded to the tensor's point dimension and outputs past the valid length are 0.
 
     ``exact_only`` selects the difference-form kernel on every pair instead of screen + exact re-check
     (same output bits; default from the URED_EXACT_ONLY=1 environment knob, used for A/B timing).
@@ -55,15 +67,16 @@ def nn_forward(xyz1, xyz2, exact_only=None):
     ws_bytes = lib.ured_chamfer_workspace_bytes(B, n, m)
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
     flags = _native.URED_FLAG_EXACT_ONLY if exact_only else 0
+    len1, len2 = _len_arg("len1", len1, B, dev), _len_arg("len2", len2, B, dev)
     with torch.cuda.device(dev):
-        rc = lib.ured_chamfer_forward(_native.ptr(xyz1), _native.ptr(xyz2), B, n, m,
+        rc = lib.ured_chamfer_forward(_native.ptr(xyz1), _native.ptr(xyz2), B, n, m, _native.ptr(len1), _native.ptr(len2),
                                       _native.ptr(dist1), _native.ptr(dist2), _native.ptr(idx1), _native.ptr(idx2),
                                       _native.ptr(ws), ws_bytes, flags, _stream(dev))
     _native.check(rc, "ured_chamfer_forward")
     return dist1, dist2, idx1, idx2
 
 
-def nn_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2):
+def nn_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2, len1=None, len2=None):
     """Raw backward: (gradxyz1, gradxyz2); either upstream gradient may be None."""
     lib = _native.load()
     B, n, _ = xyz1.shape
@@ -73,6 +86,7 @@ def nn_backward(xyz1, xyz2, graddist1, graddist2, idx1, idx2):
     gradxyz2 = torch.empty_like(xyz2)
     with torch.cuda.device(dev):
         rc = lib.ured_chamfer_backward(_native.ptr(xyz1), _native.ptr(xyz2), B, n, m, 1, max(B, 1),
+                                       _native.ptr(_len_arg("len1", len1, B, dev)), _native.ptr(_len_arg("len2", len2, B, dev)),
                                        _native.ptr(graddist1), _native.ptr(graddist2),
                                        _native.ptr(idx1), _native.ptr(idx2),
                                        _native.ptr(gradxyz1), _native.ptr(gradxyz2), _stream(dev))

@@ -11,7 +11,7 @@ import torch
 from torch.autograd import Function
 
 from . import _native
-from .dist_chamfer_3D import _require_cloud, _stream, chamfer_3DDist, nn_forward
+from .dist_chamfer_3D import _len_arg, _require_cloud, _stream, chamfer_3DDist, nn_forward
 
 
 def fscore(dist1, dist2, threshold=0.0001):
@@ -29,17 +29,21 @@ def fscore(dist1, dist2, threshold=0.0001):
 class _ChamferDCD(Function):
     """chamfer(gt, x) + the calc_cd/calc_dcd epilogue as one autograd node.
 
-    forward(x, gt, alpha, n_lambda, frac_12, frac_21)
+    forward(x, gt, alpha, n_lambda, frac_12, frac_21, len_x=None, len_gt=None, non_reg=False)
         -> (loss, cd_p, cd_t, dist1, dist2, idx1, idx2)   with cloud 1 = gt, cloud 2 = x
+    len_x / len_gt: optional valid point counts per sample (ragged batches); the means then run over the valid
+    points and the DCD fractions are rebuilt per sample from the lengths.
     """
 
     @staticmethod
-    def forward(ctx, x, gt, alpha, n_lambda, frac_12, frac_21):
+    def forward(ctx, x, gt, alpha, n_lambda, frac_12, frac_21, len_x=None, len_gt=None, non_reg=False):
         lib = _native.load()
-        dist1, dist2, idx1, idx2 = nn_forward(gt, x)
-        B, n1 = dist1.shape
-        n2 = dist2.shape[1]
+        B = x.shape[0]
         dev = x.device
+        len1, len2 = _len_arg("len_gt", len_gt, B, dev), _len_arg("len_x", len_x, B, dev)
+        dist1, dist2, idx1, idx2 = nn_forward(gt, x, len1=len1, len2=len2)
+        n1 = dist1.shape[1]
+        n2 = dist2.shape[1]
         loss = torch.empty(B, device=dev, dtype=torch.float32)
         cd_p = torch.empty(B, device=dev, dtype=torch.float32)
         cd_t = torch.empty(B, device=dev, dtype=torch.float32)
@@ -47,11 +51,14 @@ class _ChamferDCD(Function):
         ew2 = torch.empty_like(dist2)
         with torch.cuda.device(dev):
             rc = lib.ured_dcd_forward(_native.ptr(dist1), _native.ptr(dist2), _native.ptr(idx1), _native.ptr(idx2),
-                                      B, n1, n2, float(alpha), float(n_lambda), float(frac_12), float(frac_21),
+                                      B, n1, n2, 1, max(B, 1), _native.ptr(len1), _native.ptr(len2),
+                                      float(alpha), float(n_lambda), float(frac_12), float(frac_21),
+                                      _native.URED_FLAG_NON_REG if non_reg else 0,
                                       _native.ptr(loss), _native.ptr(cd_p), _native.ptr(cd_t),
                                       _native.ptr(ew1), _native.ptr(ew2), _stream(dev))
         _native.check(rc, "ured_dcd_forward")
         ctx.alpha = float(alpha)
+        ctx.lens = (len1, len2)
         ctx.save_for_backward(x, gt, dist1, dist2, idx1, idx2, ew1, ew2)
         ctx.mark_non_differentiable(idx1, idx2)
         ctx.set_materialize_grads(False)
@@ -73,23 +80,24 @@ class _ChamferDCD(Function):
         grad_x = torch.empty_like(x)
         with torch.cuda.device(dev):
             rc = lib.ured_dcd_backward(_native.ptr(gt), _native.ptr(x), B, n1, n2, 1, max(B, 1),
+                                       _native.ptr(ctx.lens[0]), _native.ptr(ctx.lens[1]),
                                        _native.ptr(dist1), _native.ptr(dist2), _native.ptr(idx1), _native.ptr(idx2),
                                        _native.ptr(ew1), _native.ptr(ew2), ctx.alpha,
                                        _native.ptr(g_loss), _native.ptr(g_cd_p), _native.ptr(g_cd_t),
                                        _native.ptr(g_dist1), _native.ptr(g_dist2),
                                        _native.ptr(grad_gt), _native.ptr(grad_x), _stream(dev))
         _native.check(rc, "ured_dcd_backward")
-        return grad_x, grad_gt, None, None, None, None
+        return grad_x, grad_gt, None, None, None, None, None, None, None
 
 
-def _fused(x, gt, alpha, n_lambda, frac_12, frac_21):
+def _fused(x, gt, alpha, n_lambda, frac_12, frac_21, len_x=None, len_gt=None, non_reg=False):
     _require_cloud("x", x)
     _require_cloud("gt", gt)
     if x.shape[0] != gt.shape[0]:
         raise AssertionError(f"batch mismatch: {x.shape[0]} vs {gt.shape[0]}")  # model_utils.py:18 is an assert
     if x.shape[1] == 0 or gt.shape[1] == 0:
         raise ValueError("calc_cd / calc_dcd need non-empty clouds")
-    return _ChamferDCD.apply(x.contiguous(), gt.contiguous(), alpha, n_lambda, frac_12, frac_21)
+    return _ChamferDCD.apply(x.contiguous(), gt.contiguous(), alpha, n_lambda, frac_12, frac_21, len_x, len_gt, non_reg)
 
 
 def calc_dcd(x, gt, alpha=1000, n_lambda=1, return_raw=False, non_reg=False):
@@ -136,3 +144,14 @@ def calc_cd(output, gt, calc_f1=False, return_raw=False, normalize=False, separa
     if return_raw:
         res.extend([dist1, dist2, idx1, idx2])
     return res
+
+
+def chamfer_ragged(x, gt, len_x=None, len_gt=None, alpha=1000, n_lambda=1, non_reg=False):
+    """Batched Chamfer/DCD over padded ragged clouds: sample b uses x[b, :len_x[b]] and gt[b, :len_gt[b]].
+
+    Returns ``(loss, cd_p, cd_t, dist1, dist2, idx1, idx2)`` exactly as ``calc_dcd(..., return_raw=True)`` would for
+    each sample on its own slices (entries past a sample's length are 0; a sample with an empty side gets zeros).
+    The lengths may be device tensors -- no host synchronisation happens here.  This is the batched form of the
+    per-sample loop in loss/chamfer_loss.py:13-30.
+    """
+    return _fused(x.float(), gt.float(), alpha, n_lambda, 1.0, 1.0, len_x, len_gt, non_reg)

@@ -38,7 +38,7 @@ class PackedClouds:
         nbytes = lib.ured_packed_bytes(self.count, self.n)
         self.packed = torch.empty(nbytes, device=self.xyz.device, dtype=torch.uint8)
         with torch.cuda.device(self.xyz.device):
-            rc = lib.ured_pack_clouds(_native.ptr(self.xyz), self.count, self.n, _native.ptr(self.packed),
+            rc = lib.ured_pack_clouds(_native.ptr(self.xyz), self.count, self.n, None, _native.ptr(self.packed),
                                       _stream(self.xyz.device))
         _native.check(rc, "ured_pack_clouds")
 
@@ -83,7 +83,7 @@ def nn_pairs(cloud1, cloud2, B, rep1, mod2, exact_only=False):
     with torch.cuda.device(dev):
         rc = lib.ured_nn_packed(_native.ptr(c1.xyz), _native.ptr(c1.packed), n1,
                                 _native.ptr(c2.xyz), _native.ptr(c2.packed), n2,
-                                B, rep1, mod2,
+                                B, rep1, mod2, None, None,
                                 _native.ptr(dist1), _native.ptr(dist2), _native.ptr(idx1), _native.ptr(idx2),
                                 _native.ptr(scratch), scratch_bytes, flags, _stream(dev))
     _native.check(rc, "ured_nn_packed")
@@ -99,7 +99,8 @@ def pair_scores(dist1, dist2, idx1, idx2, alpha=1000, n_lambda=1):
     out = torch.empty(3, B, device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         rc = lib.ured_dcd_forward(_native.ptr(dist1), _native.ptr(dist2), _native.ptr(idx1), _native.ptr(idx2),
-                                  B, n1, n2, float(alpha), float(n_lambda), float(n2 / n1), float(n1 / n2),
+                                  B, n1, n2, 1, max(B, 1), None, None,
+                                  float(alpha), float(n_lambda), float(n2 / n1), float(n1 / n2), 0,
                                   _native.ptr(out[0]), _native.ptr(out[1]), _native.ptr(out[2]),
                                   None, None, _stream(dev))
     _native.check(rc, "ured_dcd_forward")

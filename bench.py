@@ -192,11 +192,14 @@ def run_retrieval(args):
     Q = args.queries or Q
     k = 10
     lo, hi = ured.shard_bounds(S, world, rank)
-    # the library shard is generated in slabs (seeded by global shape id range), packed once and kept resident
+    # the library is defined in global slabs of 512 shapes (seed = slab id), so every world size sees the SAME
+    # library; a rank generates the slabs overlapping its shard, packs the shard once and keeps it resident
+    SLAB = 512
     slabs = []
-    for s0 in range(lo, hi, 4096):
-        x, _ = synth(min(4096, hi - s0), n, 8, seed=7000 + s0)
-        slabs.append(x.to(dev))
+    for sid in range(lo // SLAB, (hi + SLAB - 1) // SLAB if hi > lo else 0):
+        x, _ = synth(SLAB, n, 8, seed=7000 + sid)
+        a, b = max(lo, sid * SLAB) - sid * SLAB, min(hi, (sid + 1) * SLAB) - sid * SLAB
+        slabs.append(x[a:b].to(dev))
     shard = ured.PackedClouds(torch.cat(slabs)) if slabs else None
     del slabs
     _, tg_host = synth(Q, 8, n, seed=99)      # same targets on every rank
@@ -415,7 +418,7 @@ def main():
 
     def nn_only():
         rc = lib.ured_nn_packed(gt_dev.data_ptr(), pk_gt.packed.data_ptr(), n_gt,
-                                x_dev.data_ptr(), pk_x.packed.data_ptr(), n_x, B, 1, B,
+                                x_dev.data_ptr(), pk_x.packed.data_ptr(), n_x, B, 1, B, None, None,
                                 d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
                                 scratch.data_ptr(), scratch_bytes, flags, stream)
         ured._native.check(rc, "ured_nn_packed")

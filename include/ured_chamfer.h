@@ -59,6 +59,14 @@ extern "C" {
 
 /* flags for the forward entry points */
 #define URED_FLAG_EXACT_ONLY 1u /* skip the 3-FFMA screening pass; run the difference-form kernel on every pair */
+#define URED_FLAG_NON_REG    2u /* ured_dcd_forward with lengths: clamp the DCD fractions at 1 (calc_dcd non_reg=True) */
+
+/* Ragged batches.  Entry points that take `len1` / `len2` (device int32 arrays, one entry per cloud-1 / cloud-2
+ * entry, or NULL) treat cloud c as having only its first len[c] points (clamped to [0, n]); n is then the row
+ * stride.  Outputs past a cloud's valid length are written as 0; a pair with an empty side yields zeros, like the
+ * reference op which never touches its zero-filled outputs then.  This is what lets U-RED's per-sample / per-part
+ * loop (loss/chamfer_loss.py:13-30, sizes mask.sum(1)*1024 and ragged target parts) run as two batched calls with
+ * the lengths staying on the device. */
 
 int ured_abi_version(void);
 const char *ured_last_error_string(void);
@@ -74,7 +82,7 @@ unsigned long long ured_kernel_launches(void);
  * (block stride = ured_packed_bytes(1, n) rounded down to (4*np + 32) * 4 bytes), so a library that
  * is scored against many targets is packed once, kept resident, and addressed by slices. */
 size_t ured_packed_bytes(int count, int n);
-int ured_pack_clouds(const float *xyz, int count, int n, void *packed, void *stream);
+int ured_pack_clouds(const float *xyz, int count, int n, const int *len, void *packed, void *stream);
 
 /* ---- nearest neighbours on packed clouds (both directions, one launch) --------------------
  * dist1/idx1: [B, n1]  for every point of cloud 1, squared distance to / index of its nearest
@@ -87,7 +95,7 @@ int ured_pack_clouds(const float *xyz, int count, int n, void *packed, void *str
 size_t ured_nn_scratch_bytes(int B, int n1, int n2);
 int ured_nn_packed(const float *xyz1, const void *packed1, int n1,
                    const float *xyz2, const void *packed2, int n2,
-                   int B, int rep1, int mod2,
+                   int B, int rep1, int mod2, const int *len1, const int *len2,
                    float *dist1, float *dist2, int *idx1, int *idx2,
                    void *scratch, size_t scratch_bytes,
                    unsigned flags, void *stream);
@@ -96,6 +104,7 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1,
  * workspace: ured_chamfer_workspace_bytes(B, n1, n2) bytes, 256-byte aligned. */
 size_t ured_chamfer_workspace_bytes(int B, int n1, int n2);
 int ured_chamfer_forward(const float *xyz1, const float *xyz2, int B, int n1, int n2,
+                         const int *len1, const int *len2,
                          float *dist1, float *dist2, int *idx1, int *idx2,
                          void *workspace, size_t workspace_bytes,
                          unsigned flags, void *stream);
@@ -105,7 +114,7 @@ int ured_chamfer_forward(const float *xyz1, const float *xyz2, int B, int n1, in
  * accumulates into caller-zeroed buffers; here the zero-fill is part of the call).
  * graddist1 / graddist2 may be NULL (treated as zeros). */
 int ured_chamfer_backward(const float *xyz1, const float *xyz2, int B, int n1, int n2,
-                          int rep1, int mod2,
+                          int rep1, int mod2, const int *len1, const int *len2,
                           const float *graddist1, const float *graddist2,
                           const int *idx1, const int *idx2,
                           float *gradxyz1, float *gradxyz2, void *stream);
@@ -121,8 +130,8 @@ int ured_chamfer_backward(const float *xyz1, const float *xyz2, int B, int n1, i
  * ew1 [B, n1] / ew2 [B, n2] (optional, may be NULL) receive exp(-alpha d) * w per point, the
  * only per-point state the backward pass needs.  Sums are accumulated in float64. */
 int ured_dcd_forward(const float *dist1, const float *dist2, const int *idx1, const int *idx2,
-                     int B, int n1, int n2,
-                     float alpha, float n_lambda, float frac_12, float frac_21,
+                     int B, int n1, int n2, int rep1, int mod2, const int *len1, const int *len2,
+                     float alpha, float n_lambda, float frac_12, float frac_21, unsigned flags,
                      float *loss, float *cd_p, float *cd_t,
                      float *ew1, float *ew2, void *stream);
 
@@ -131,7 +140,7 @@ int ured_dcd_forward(const float *dist1, const float *dist2, const int *idx1, co
  * same pass.  Any of g_loss/g_cd_p/g_cd_t [B] and g_dist1 [B,n1] / g_dist2 [B,n2] may be NULL.
  * ew1/ew2 are required when g_loss is given.  gradxyz1/gradxyz2 are overwritten. */
 int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n2,
-                      int rep1, int mod2,
+                      int rep1, int mod2, const int *len1, const int *len2,
                       const float *dist1, const float *dist2, const int *idx1, const int *idx2,
                       const float *ew1, const float *ew2, float alpha,
                       const float *g_loss, const float *g_cd_p, const float *g_cd_t,

@@ -21,7 +21,7 @@ def declared_symbols():
 def test_header_symbols_are_exported(ured):
     lib = ctypes.CDLL(ured._native.LIB_PATH)
     syms = declared_symbols()
-    assert len(syms) >= 11
+    assert len(syms) >= 14
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/ but not exported"
     assert set(syms) == set(ured._native.EXPORTED_SYMBOLS), "ctypes binding and header disagree"
@@ -41,14 +41,14 @@ def test_abi_version_and_sizes(ured):
 def test_argument_errors_do_not_need_a_device(ured):
     lib = ured._native.load()
     E_NULL, E_SHAPE, E_RANGE = -1, -2, -4
-    assert lib.ured_chamfer_forward(None, None, 2, 8, 8, None, None, None, None, None, 0, 0, None) == E_NULL
+    assert lib.ured_chamfer_forward(None, None, 2, 8, 8, None, None, None, None, None, None, None, 0, 0, None) == E_NULL
     assert b"NULL" in lib.ured_last_error_string()
-    assert lib.ured_chamfer_forward(None, None, -1, 8, 8, None, None, None, None, None, 0, 0, None) == E_SHAPE
-    assert lib.ured_nn_packed(None, None, 8, None, None, 8, 4, 0, 4, None, None, None, None, None, 0, 0, None) == E_SHAPE
+    assert lib.ured_chamfer_forward(None, None, -1, 8, 8, None, None, None, None, None, None, None, 0, 0, None) == E_SHAPE
+    assert lib.ured_nn_packed(None, None, 8, None, None, 8, 4, 0, 4, None, None, None, None, None, None, None, 0, 0, None) == E_SHAPE
     assert lib.ured_topk_smallest(None, 1, 5, 6, 0, None, None, None) == E_RANGE
-    assert lib.ured_dcd_forward(None, None, None, None, 1, 8, 8, 1.0, 1.0, 1.0, 1.0, None, None, None, None, None, None) == E_NULL
+    assert lib.ured_dcd_forward(None, None, None, None, 1, 8, 8, 1, 1, None, None, 1.0, 1.0, 1.0, 1.0, 0, None, None, None, None, None, None) == E_NULL
     # empty batches are a successful no-op
-    assert lib.ured_chamfer_forward(None, None, 0, 8, 8, None, None, None, None, None, 0, 0, None) == 0
+    assert lib.ured_chamfer_forward(None, None, 0, 8, 8, None, None, None, None, None, None, None, 0, 0, None) == 0
     assert lib.ured_topk_smallest(None, 0, 5, 2, 0, None, None, None) == 0
 
 

@@ -287,3 +287,53 @@ def test_stream_and_error_behaviour(ured):
     assert empty[0].shape == (0, 400)
     z = ured.chamfer_3DDist()(a, b[:, :0])  # empty opposing cloud: the reference leaves its zero-filled outputs
     assert (z[0] == 0).all() and (z[2] == 0).all() and z[1].shape == (2, 0)
+
+
+@pytest.mark.parametrize("alpha,lam,non_reg", [(1000, 1, False), (60, 0.5, True), (0.0, 1, False)])
+def test_ragged_batches_match_per_sample_calls(ured, oracle, alpha, lam, non_reg):
+    """chamfer_ragged(x, gt, len_x, len_gt) == calc_dcd on each sample's own slices (values, raw outputs, gradients)."""
+    B, NX, NG = 6, 1536, 1100
+    x0, gt0 = make_clouds(110, B, NX, "S"), make_clouds(111, B, NG, "S") * 0.9
+    len_x = torch.tensor([1536, 1024, 1, 700, 33, 0], dtype=torch.int32)
+    len_gt = torch.tensor([1100, 5, 640, 1100, 0, 77], dtype=torch.int32)
+    w = torch.linspace(0.5, 1.5, B)
+    x, gt = dev(x0).requires_grad_(), dev(gt0).requires_grad_()
+    loss, cd_p, cd_t, d1, d2, i1, i2 = ured.chamfer_ragged(x, gt, dev(len_x), dev(len_gt), alpha=alpha, n_lambda=lam, non_reg=non_reg)
+    ((loss + 2.0 * cd_t) * dev(w)).sum().backward()
+    torch.cuda.synchronize()
+    gx, ggt = x.grad.cpu(), gt.grad.cpu()
+    for b in range(B):
+        lx, lg = int(len_x[b]), int(len_gt[b])
+        assert (d1[b, lg:] == 0).all() and (i1[b, lg:] == 0).all() and (d2[b, lx:] == 0).all()
+        assert (gx[b, lx:] == 0).all() and (ggt[b, lg:] == 0).all()
+        if lx == 0 or lg == 0:
+            assert loss[b] == 0 and cd_t[b] == 0 and (d1[b] == 0).all() and (d2[b] == 0).all()
+            assert (gx[b] == 0).all() and (ggt[b] == 0).all()
+            continue
+        xo, gto = x0[b:b + 1, :lx].clone().requires_grad_(), gt0[b:b + 1, :lg].clone().requires_grad_()
+        ol, op, ot, od1, od2, oi1, oi2 = oracle.t.calc_dcd_oracle(xo, gto, alpha=alpha, n_lambda=lam, return_raw=True, non_reg=non_reg)
+        assert np.array_equal(i1[b, :lg].cpu().numpy(), oi1[0].numpy()) and np.array_equal(i2[b, :lx].cpu().numpy(), oi2[0].numpy())
+        assert np.array_equal(d1[b, :lg].detach().cpu().numpy(), od1[0].detach().numpy())
+        assert np.array_equal(d2[b, :lx].detach().cpu().numpy(), od2[0].detach().numpy())
+        for got, want in [(loss[b], ol[0]), (cd_p[b], op[0]), (cd_t[b], ot[0])]:
+            assert np.isclose(got.item(), want.item(), rtol=RTOL, atol=1e-12)
+        ((ol + 2.0 * ot) * w[b]).sum().backward()
+        assert rel_err(gx[b, :lx].numpy(), xo.grad[0].numpy()) < RTOL
+        assert rel_err(ggt[b, :lg].numpy(), gto.grad[0].numpy()) < RTOL
+
+
+def test_compute_cm_loss_has_no_per_sample_launches(ured):
+    """The batched compute_cm_loss issues a fixed number of kernels, independent of batch size and part count."""
+    lib = ured._native.load()
+
+    def launches(B, P):
+        src = dev(make_clouds(120, B, P * 1024, "S")).requires_grad_()
+        tgt = dev(make_clouds(121, B, 2048, "S"))
+        parts = [[dev(make_clouds(122 + i, 1, 50 + 13 * i, "S")[0]) for i in range(P)] for _ in range(B)]
+        mask = torch.ones(B, P, dtype=torch.int64, device="cuda")
+        n0 = lib.ured_kernel_launches()
+        full, part = ured.compute_cm_loss(src, tgt, parts, mask)
+        (full + part).backward()
+        torch.cuda.synchronize()
+        return lib.ured_kernel_launches() - n0
+    assert launches(2, 2) == launches(8, 4)
