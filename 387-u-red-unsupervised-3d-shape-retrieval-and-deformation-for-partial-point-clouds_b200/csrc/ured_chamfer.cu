@@ -781,14 +781,15 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (B == 0 || (n1 == 0 && n2 == 0)) return 0;
-    if ((n1 && (!dist1 || !idx1)) || (n2 && (!dist2 || !idx2))) return fail_arg(URED_E_NULL, "ured_nn_packed: NULL output");
+    const bool skip2 = (flags & URED_FLAG_ONE_DIRECTION) != 0;
+    if ((n1 && (!dist1 || !idx1)) || (n2 && !skip2 && (!dist2 || !idx2))) return fail_arg(URED_E_NULL, "ured_nn_packed: NULL output");
     if (n1 == 0 || n2 == 0) {
         // the reference kernel never writes when the opposing cloud is empty: zeros stay zeros
         if (n1) { URED_CUDA(cudaMemsetAsync(dist1, 0, (size_t)B * n1 * 4, st), "memset"); URED_CUDA(cudaMemsetAsync(idx1, 0, (size_t)B * n1 * 4, st), "memset"); }
-        if (n2) { URED_CUDA(cudaMemsetAsync(dist2, 0, (size_t)B * n2 * 4, st), "memset"); URED_CUDA(cudaMemsetAsync(idx2, 0, (size_t)B * n2 * 4, st), "memset"); }
+        if (n2 && !skip2) { URED_CUDA(cudaMemsetAsync(dist2, 0, (size_t)B * n2 * 4, st), "memset"); URED_CUDA(cudaMemsetAsync(idx2, 0, (size_t)B * n2 * 4, st), "memset"); }
         return 0;
     }
-    if (!xyz1 || !xyz2 || !packed1 || !packed2) return fail_arg(URED_E_NULL, "ured_nn_packed: NULL input");
+    if (!xyz1 || !xyz2 || (!packed1 && !skip2) || !packed2) return fail_arg(URED_E_NULL, "ured_nn_packed: NULL input");
     PackedView v1 = view_packed(packed1, n1), v2 = view_packed(packed2, n2);
     NNParams p;
     p.xyz[0] = xyz1; p.xyz[1] = xyz2;
@@ -802,8 +803,9 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
     const bool exact = (flags & URED_FLAG_EXACT_ONLY) != 0;
     const NNShape sh = choose_nn_shape(B, n1, n2);
     const int R = sh.R;
+    const bool one_dir = (flags & URED_FLAG_ONE_DIRECTION) != 0;  // only cloud-1 points search cloud 2 (K=1 kNN)
     p.qtiles[0] = (n1 + R * kNNThreads - 1) / (R * kNNThreads);
-    p.qtiles[1] = (n2 + R * kNNThreads - 1) / (R * kNNThreads);
+    p.qtiles[1] = one_dir ? 0 : (n2 + R * kNNThreads - 1) / (R * kNNThreads);
     p.nsplit = sh.nsplit;
     p.B = B;
     const size_t tot1 = (size_t)B * n1, tot2 = (size_t)B * n2;
@@ -825,8 +827,10 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
     if (rc || sh.nsplit == 1) return rc;
     merge_splits_kernel<<<(unsigned)((tot1 + 255) / 256), 256, 0, st>>>(p.part_dist[0], p.part_idx[0], tot1, sh.nsplit, dist1, idx1);
     URED_COUNT_LAUNCH();
-    merge_splits_kernel<<<(unsigned)((tot2 + 255) / 256), 256, 0, st>>>(p.part_dist[1], p.part_idx[1], tot2, sh.nsplit, dist2, idx2);
-    URED_COUNT_LAUNCH();
+    if (!one_dir) {
+        merge_splits_kernel<<<(unsigned)((tot2 + 255) / 256), 256, 0, st>>>(p.part_dist[1], p.part_idx[1], tot2, sh.nsplit, dist2, idx2);
+        URED_COUNT_LAUNCH();
+    }
     return check_cuda(cudaGetLastError(), "merge_splits_kernel launch");
 }
 

@@ -159,6 +159,45 @@ def score_library(targets, library, alpha=1000, n_lambda=1, max_pairs=8192, exac
     return {"dcd": out[0], "cd_p": out[1], "cd_t": out[2]}
 
 
+def score_all_pairs(library, alpha=1000, n_lambda=1, max_pairs=8192, exact_only=False):
+    """All-pairs library scores, the batched form of `get_src_pair` (engine/generate_pair.py:69-85).
+
+    Returns a [3, S, S] tensor (dcd, cd_p, cd_t) with entry [:, idx, i] = calc_dcd(x=library[i], gt=library[idx]) for
+    i >= idx -- the row a reference pickle holds for shape idx -- and 0 below the diagonal (not evaluated).
+    """
+    lib_c = _as_packed(library)
+    S = lib_c.count
+    out = torch.zeros(3, S, S, device=lib_c.device, dtype=torch.float32)
+    rows = max(1, max_pairs // max(S, 1))
+    for q0 in range(0, S, rows):
+        q1 = min(S, q0 + rows)
+        sc = score_library(lib_c.slice(q0, q1), lib_c.slice(q0, S), alpha=alpha, n_lambda=n_lambda,
+                           max_pairs=max_pairs, exact_only=exact_only)
+        for m, key in enumerate(("dcd", "cd_p", "cd_t")):
+            out[m, q0:q1, q0:] = sc[key]
+    keep = torch.ones(S, S, device=out.device, dtype=torch.bool).triu()
+    return out * keep
+
+
+def write_pair_pickles(out_dir, names, scores):
+    """Write one `<name>.pickle` per shape in the reference's layout (engine/generate_pair.py:82-85):
+    {'dcd_loss', 'cd_s', 'cd_m'} -> float64 arrays over shapes idx..S-1, readable by read_pickle_topk
+    (dataset/dataset_utils.py:1043-1051)."""
+    import os
+    import pickle
+    import numpy as np
+    sc = scores.detach().cpu().numpy().astype(np.float64)
+    os.makedirs(out_dir, exist_ok=True)
+    paths = []
+    for idx, name in enumerate(names):
+        rec = {"dcd_loss": sc[0, idx, idx:].copy(), "cd_s": sc[1, idx, idx:].copy(), "cd_m": sc[2, idx, idx:].copy()}
+        path = os.path.join(out_dir, f"{name}.pickle")
+        with open(path, "wb") as f:
+            pickle.dump(rec, f)
+        paths.append(path)
+    return paths
+
+
 def topk_smallest(scores, k, idx_offset=0):
     """k smallest per row in ascending (score, index) order -> (values [rows,k], indices int32 [rows,k]).
 

@@ -59,6 +59,7 @@ extern "C" {
 
 /* flags for the forward entry points */
 #define URED_FLAG_EXACT_ONLY 1u /* skip the 3-FFMA screening pass; run the difference-form kernel on every pair */
+#define URED_FLAG_ONE_DIRECTION 4u /* ured_nn_packed: only cloud-1 points search cloud 2 (dist2/idx2 untouched, may be NULL) */
 #define URED_FLAG_NON_REG    2u /* ured_dcd_forward with lengths: clamp the DCD fractions at 1 (calc_dcd non_reg=True) */
 
 /* Ragged batches.  Entry points that take `len1` / `len2` (device int32 arrays, one entry per cloud-1 / cloud-2

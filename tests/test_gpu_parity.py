@@ -337,3 +337,58 @@ def test_compute_cm_loss_has_no_per_sample_launches(ured):
         torch.cuda.synchronize()
         return lib.ured_kernel_launches() - n0
     assert launches(2, 2) == launches(8, 4)
+
+
+def test_knn1_and_residual_retrieval_loss(ured, oracle):
+    """K=1 kNN (loss/basic_loss.py:249-265's knn_points call) on the one-direction NN kernel, ragged source lengths."""
+    B, N, P = 3, 700, 3
+    x0, src0 = make_clouds(130, B, N, "S"), make_clouds(131, B, P * 1024, "S")
+    res0 = 0.01 * torch.randn(B, N, 3, generator=torch.Generator().manual_seed(3))
+    mask = torch.tensor([[1, 1, 1], [1, 0, 0], [1, 1, 0]])
+    x, src, res = dev(x0).requires_grad_(), dev(src0).requires_grad_(), dev(res0).requires_grad_()
+    loss, reg = ured.residual_retrieval_loss(x, src, res, dev(mask))
+    (loss + reg).backward()
+    xo, so, ro = x0.clone().requires_grad_(), src0.clone().requires_grad_(), res0.clone().requires_grad_()
+    nn_all = []
+    for b in range(B):
+        cnt = int(mask[b].sum()) * 1024
+        d1, _, i1, _ = oracle.t.oracle_cd(xo[b:b + 1], so[b:b + 1, :cnt])
+        nn_all.append(so[b, :cnt][i1[0].long()])
+        dists, idx, nn = ured.knn1_points(dev(x0[b:b + 1]), dev(src0[b:b + 1, :cnt]))
+        assert np.array_equal(idx[0, :, 0].cpu().numpy(), i1[0].numpy().astype(np.int64))
+        assert np.array_equal(dists[0, :, 0].cpu().numpy(), d1[0].detach().numpy())
+    want = torch.mean(torch.sum(torch.abs(xo + ro - torch.stack(nn_all)), dim=-1))
+    want_reg = torch.mean(torch.sum(torch.abs(ro), dim=-1))
+    (want + want_reg).backward()
+    assert np.isclose(loss.item(), want.item(), rtol=RTOL) and np.isclose(reg.item(), want_reg.item(), rtol=RTOL)
+    assert rel_err(src.grad.cpu().numpy(), so.grad.numpy()) < RTOL and rel_err(x.grad.cpu().numpy(), xo.grad.numpy()) < RTOL
+    # distances are differentiable in both clouds
+    a, b_ = dev(x0).requires_grad_(), dev(src0[:, :1024]).requires_grad_()
+    d, _, _ = ured.knn1_points(a, b_, return_nn=False)
+    d.sum().backward()
+    e1, _, j1, _ = oracle.c.chamfer_forward(x0.numpy(), src0[:, :1024].numpy())
+    r1, r2 = oracle.c.chamfer_backward_f64(x0.numpy(), src0[:, :1024].numpy(), np.ones((B, N), np.float32), np.zeros((B, 1024), np.float32), j1,
+                                           np.zeros((B, 1024), np.int32))
+    assert rel_err(a.grad.cpu().numpy(), r1) < RTOL and rel_err(b_.grad.cpu().numpy(), r2) < RTOL
+
+
+def test_all_pairs_and_pickle_layout(ured, oracle, tmp_path):
+    """score_all_pairs == the reference's get_src_pair rows (engine/generate_pair.py:69-85), pickles readable its way."""
+    import pickle
+    S, M = 9, 400
+    libr = make_clouds(140, S, M, "S") * torch.linspace(0.7, 1.1, S).view(S, 1, 1)
+    sc = ured.score_all_pairs(dev(libr), max_pairs=20)
+    names = [f"shape{i}" for i in range(S)]
+    paths = ured.write_pair_pickles(str(tmp_path), names, sc)
+    for idx in [0, 4, 8]:
+        rec = pickle.load(open(paths[idx], "rb"))
+        assert set(rec) == {"dcd_loss", "cd_s", "cd_m"} and rec["cd_m"].shape == (S - idx,) and rec["cd_m"].dtype == np.float64
+        l, p, t = oracle.t.calc_dcd_oracle(libr[idx:], libr[idx:idx + 1].expand(S - idx, M, 3))
+        assert np.allclose(rec["dcd_loss"], l.numpy(), rtol=RTOL) and np.allclose(rec["cd_s"], p.numpy(), rtol=RTOL)
+        assert np.allclose(rec["cd_m"], t.numpy(), rtol=RTOL)
+        # dataset_utils.read_pickle_topk: torch.topk(torch.tensor(data['cd_m']), k, largest=False)
+        k = min(3, S - idx)
+        want = torch.sort(t, stable=True).indices[:k]
+        got = ured.topk_smallest(dev(torch.tensor(rec["cd_m"], dtype=torch.float32)), k)[1]
+        assert got.cpu().tolist() == want.tolist()
+    assert (sc[:, 5, :5] == 0).all()
