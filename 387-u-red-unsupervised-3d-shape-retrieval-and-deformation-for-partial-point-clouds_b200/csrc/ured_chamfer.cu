@@ -72,13 +72,19 @@ constexpr int kPackTail = 32;  // floats after X|Y|Z|W of each cloud: [0] = max 
 inline size_t cloud_stride(int np) { return (size_t)np * 4 + kPackTail; }
 
 // one CTA per cloud; writes the cloud's block X|Y|Z|W (each np floats) | tail (max W)
-// len (optional): number of valid points of each cloud (ragged batches); everything past it replicates the last valid point
-__global__ void __launch_bounds__(kPackThreads) pack_kernel(const float *__restrict__ xyz, int n_max, int np,
-                                                            float *__restrict__ soa, const int *__restrict__ len) {
-    const size_t cloud = blockIdx.x;
+// len (optional): number of valid points of each cloud (ragged batches); everything past it replicates the last valid point.
+// One launch can pack two cloud sets (the two sides of a Chamfer call): blocks [0, count_a) take set a, the rest set b.
+struct PackSet { const float *xyz; float *soa; const int *len; int n_max, np; };
+
+__global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackSet a, const PackSet bset, int count_a) {
+    const bool second = (int)blockIdx.x >= count_a;
+    const PackSet &ps = second ? bset : a;
+    const size_t cloud = second ? blockIdx.x - count_a : blockIdx.x;
+    const int n_max = ps.n_max, np = ps.np;
+    const int *__restrict__ len = ps.len;
     const int n = len ? max(1, min(len[cloud], n_max)) : n_max;  // (an empty cloud is never read as candidates)
-    const float *src = xyz + cloud * (size_t)n_max * 3;
-    float *X = soa + cloud * ((size_t)np * 4 + kPackTail);
+    const float *src = ps.xyz + cloud * (size_t)n_max * 3;
+    float *X = ps.soa + cloud * ((size_t)np * 4 + kPackTail);
     float *Y = X + np, *Z = Y + np, *W = Z + np;
     float *wmax = W + np;
     float m = 0.0f;
@@ -150,7 +156,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 // nearest-neighbour kernel
 // ------------------------------------------------------------------------------------------
 constexpr int kNNThreads = 128;  // 4 warps, one per SM sub-partition; 5-6 CTAs resident per SM
-constexpr int kTile = 1024;      // candidates per shared-memory stage
+constexpr int kTile = 1024;      // candidates per shared-memory stage (768 was tried: 7 CTAs/SM but 3% slower on cfg2)
 constexpr int kStages = 2;
 constexpr int kChunk = 32;       // candidates per running-minimum chunk (= the padding granule of the packed image)
 constexpr float kInf = __builtin_huge_valf();
@@ -341,20 +347,27 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
     for (int r = 0; r < R; r++) {
         const float oqx = kUnscale * qx[r], oqy = kUnscale * qy[r], oqz = kUnscale * qz[r];
         const int c = min(bchunk[r], ncp - G);  // (an empty trailing split re-reads the last chunk; its result loses every merge)
+        // Exact difference form on the chunk's G candidates (packed math, same bits as exact_d).  Entries past nc
+        // replicate point nc-1, so they can tie with it but sit at higher indices and never win.
+        const float nq1 = SCREEN ? 0.5f : 1.0f;  // registers hold -2q (SCREEN) or -q (EXACT); both rescalings are exact
+        const float2 nqx = make_float2(nq1 * qx[r], nq1 * qx[r]), nqy = make_float2(nq1 * qy[r], nq1 * qy[r]),
+                     nqz = make_float2(nq1 * qz[r], nq1 * qz[r]);
         float bd = 0.0f;
         int bi = c;
 #pragma unroll
         for (int k = 0; k < G; k += 4) {
-            // entries past nc replicate point nc-1 and can therefore never be strictly smaller
             const float4 x4 = *reinterpret_cast<const float4 *>(gX + c + k);
             const float4 y4 = *reinterpret_cast<const float4 *>(gY + c + k);
             const float4 z4 = *reinterpret_cast<const float4 *>(gZ + c + k);
-            const float d0 = exact_d(x4.x, y4.x, z4.x, oqx, oqy, oqz), d1 = exact_d(x4.y, y4.y, z4.y, oqx, oqy, oqz);
-            const float d2 = exact_d(x4.z, y4.z, z4.z, oqx, oqy, oqz), d3 = exact_d(x4.w, y4.w, z4.w, oqx, oqy, oqz);
-            if (k == 0 || d0 < bd) { bd = d0; bi = c + k; }
-            if (d1 < bd) { bd = d1; bi = c + k + 1; }
-            if (d2 < bd) { bd = d2; bi = c + k + 2; }
-            if (d3 < bd) { bd = d3; bi = c + k + 3; }
+            const float2 dx0 = __fadd2_rn(make_float2(x4.x, x4.y), nqx), dx1 = __fadd2_rn(make_float2(x4.z, x4.w), nqx);
+            const float2 dy0 = __fadd2_rn(make_float2(y4.x, y4.y), nqy), dy1 = __fadd2_rn(make_float2(y4.z, y4.w), nqy);
+            const float2 dz0 = __fadd2_rn(make_float2(z4.x, z4.y), nqz), dz1 = __fadd2_rn(make_float2(z4.z, z4.w), nqz);
+            const float2 d01 = __ffma2_rn(dz0, dz0, __ffma2_rn(dx0, dx0, __fmul2_rn(dy0, dy0)));
+            const float2 d23 = __ffma2_rn(dz1, dz1, __ffma2_rn(dx1, dx1, __fmul2_rn(dy1, dy1)));
+            if (k == 0 || d01.x < bd) { bd = d01.x; bi = c + k; }   // strict '<' in ascending order: lowest index wins
+            if (d01.y < bd) { bd = d01.y; bi = c + k + 1; }
+            if (d23.x < bd) { bd = d23.x; bi = c + k + 2; }
+            if (d23.y < bd) { bd = d23.y; bi = c + k + 3; }
         }
         if (SCREEN) {
             // |s + |q|^2 - d_fp32| <= 11.02 u S^2 with S = |q| + max|c| (DESIGN.md "screening bound");
@@ -633,15 +646,16 @@ __global__ void __launch_bounds__(kGradSmemThreads) grad_smem_kernel(const GradP
     for (int k = threadIdx.x; k < total3; k += kGradSmemThreads) acc[k] = 0.0f;
     __syncthreads();
     const float *xyz1 = p.xyz[0] + b * n1 * 3, *xyz2 = p.xyz[1] + b * n2 * 3;
+    const int v1 = valid_len(p.len[0], b, n1), v2 = valid_len(p.len[1], b, n2);
+    // (shared-memory float atomicAdd is a CAS loop on sm_100 -- ATOMS.CAST.SPIN -- but with ~1 hit per target point it
+    //  still beats zero-fill + global RED: 51 us vs 81 us on cfg2; an unrolled, load-first variant measured no better)
     for (int t = threadIdx.x; t < n1 + n2; t += kGradSmemThreads) {
         const int side = t >= n1 ? 1 : 0;
         const int j = side ? t - n1 : t;
         const int n_own = side ? n2 : n1;
+        if (j >= (side ? v2 : v1) || (side ? v1 : v2) == 0) continue;
         const size_t pt = b * n_own + j;
-        const int v_own = valid_len(side ? p.len[1] : p.len[0], b, n_own);
-        const int v_oth = valid_len(side ? p.len[0] : p.len[1], b, side ? n1 : n2);
-        if (j >= v_own || v_oth == 0) continue;
-        const float gd = point_grad_coeff(p, side, b, pt, v_own);
+        const float gd = point_grad_coeff(p, side, b, pt, side ? v2 : v1);
         const int j2 = (side ? p.idx[1] : p.idx[0])[pt];
         const float *a = (side ? xyz2 : xyz1) + j * 3;
         const float *o = (side ? xyz1 : xyz2) + j2 * 3;
@@ -763,7 +777,9 @@ int ured_pack_clouds(const float *xyz, int count, int n, const int *len, void *p
     if (!xyz || !packed) return fail_arg(URED_E_NULL, "ured_pack_clouds: NULL pointer");
     if ((uintptr_t)packed % 256) return fail_arg(URED_E_WORKSPACE, "packed image must be 256-byte aligned");
     PackedView v = view_packed(packed, n);
-    pack_kernel<<<count, kPackThreads, 0, (cudaStream_t)stream>>>(xyz, n, v.np, (float *)v.soa, len);
+    PackSet a;
+    a.xyz = xyz; a.soa = (float *)v.soa; a.len = len; a.n_max = n; a.np = v.np;
+    pack_kernel<<<count, kPackThreads, 0, (cudaStream_t)stream>>>(a, a, count);
     URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "pack_kernel launch");
 }
@@ -853,10 +869,13 @@ int ured_chamfer_forward(const float *xyz1, const float *xyz2, int B, int n1, in
     }
     void *pk1 = workspace;
     void *pk2 = (char *)workspace + ured_packed_bytes(B, n1);
-    if (n1 > 0 && n2 > 0) {
-        rc = ured_pack_clouds(xyz1, B, n1, len1, pk1, stream);
-        if (rc) return rc;
-        rc = ured_pack_clouds(xyz2, B, n2, len2, pk2, stream);
+    if (n1 > 0 && n2 > 0) {  // both sides in one launch
+        PackSet a, b2;
+        a.xyz = xyz1; a.soa = (float *)pk1; a.len = len1; a.n_max = n1; a.np = pad32(n1);
+        b2.xyz = xyz2; b2.soa = (float *)pk2; b2.len = len2; b2.n_max = n2; b2.np = pad32(n2);
+        pack_kernel<<<2 * B, kPackThreads, 0, (cudaStream_t)stream>>>(a, b2, B);
+        URED_COUNT_LAUNCH();
+        rc = check_cuda(cudaGetLastError(), "pack_kernel launch");
         if (rc) return rc;
     }
     void *scratch = (char *)pk2 + ured_packed_bytes(B, n2);
