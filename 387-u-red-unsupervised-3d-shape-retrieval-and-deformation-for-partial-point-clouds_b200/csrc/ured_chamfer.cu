@@ -642,31 +642,39 @@ __global__ void __launch_bounds__(kGradSmemThreads) grad_smem_kernel(const GradP
     extern __shared__ float acc[];  // grad of cloud 1 [n1*3] | grad of cloud 2 [n2*3]
     const size_t b = blockIdx.x;
     const int n1 = p.n[0], n2 = p.n[1];
-    const int total3 = (n1 + n2) * 3;
-    for (int k = threadIdx.x; k < total3; k += kGradSmemThreads) acc[k] = 0.0f;
-    __syncthreads();
     const float *xyz1 = p.xyz[0] + b * n1 * 3, *xyz2 = p.xyz[1] + b * n2 * 3;
     const int v1 = valid_len(p.len[0], b, n1), v2 = valid_len(p.len[1], b, n2);
-    // (shared-memory float atomicAdd is a CAS loop on sm_100 -- ATOMS.CAST.SPIN -- but with ~1 hit per target point it
-    //  still beats zero-fill + global RED: 51 us vs 81 us on cfg2; an unrolled, load-first variant measured no better)
-    for (int t = threadIdx.x; t < n1 + n2; t += kGradSmemThreads) {
-        const int side = t >= n1 ? 1 : 0;
-        const int j = side ? t - n1 : t;
-        const int n_own = side ? n2 : n1;
-        if (j >= (side ? v2 : v1) || (side ? v1 : v2) == 0) continue;
-        const size_t pt = b * n_own + j;
-        const float gd = point_grad_coeff(p, side, b, pt, side ? v2 : v1);
-        const int j2 = (side ? p.idx[1] : p.idx[0])[pt];
-        const float *a = (side ? xyz2 : xyz1) + j * 3;
-        const float *o = (side ? xyz1 : xyz2) + j2 * 3;
-        const float g = __fmul_rn(gd, 2.0f);  // chamfer3D.cu:166
-        const float gx = __fmul_rn(g, __fsub_rn(a[0], o[0]));
-        const float gy = __fmul_rn(g, __fsub_rn(a[1], o[1]));
-        const float gz = __fmul_rn(g, __fsub_rn(a[2], o[2]));
-        float *own = acc + (side ? n1 * 3 : 0) + j * 3;
-        float *oth = acc + (side ? 0 : n1 * 3) + j2 * 3;
-        atomicAdd(own + 0, gx); atomicAdd(own + 1, gy); atomicAdd(own + 2, gz);
-        atomicAdd(oth + 0, -gx); atomicAdd(oth + 1, -gy); atomicAdd(oth + 2, -gz);
+    // Shared-memory float atomicAdd is a CAS loop on sm_100 (ATOMS.CAST.SPIN), so only the scatter side uses it:
+    // phase 0 STORES every point's own-side term (which also initialises the accumulators), phase 1 adds the
+    // scatter-side terms atomically.  The per-point term is recomputed in phase 1 (its loads hit L1).
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+        for (int t = threadIdx.x; t < n1 + n2; t += kGradSmemThreads) {
+            const int side = t >= n1 ? 1 : 0;
+            const int j = side ? t - n1 : t;
+            const int n_own = side ? n2 : n1;
+            float *own = acc + (side ? n1 * 3 : 0) + j * 3;
+            if (j >= (side ? v2 : v1) || (side ? v1 : v2) == 0) {
+                if (phase == 0) { own[0] = 0.0f; own[1] = 0.0f; own[2] = 0.0f; }
+                continue;
+            }
+            const size_t pt = b * n_own + j;
+            const float gd = point_grad_coeff(p, side, b, pt, side ? v2 : v1);
+            const int j2 = (side ? p.idx[1] : p.idx[0])[pt];
+            const float *a = (side ? xyz2 : xyz1) + j * 3;
+            const float *o = (side ? xyz1 : xyz2) + j2 * 3;
+            const float g = __fmul_rn(gd, 2.0f);  // chamfer3D.cu:166
+            const float gx = __fmul_rn(g, __fsub_rn(a[0], o[0]));
+            const float gy = __fmul_rn(g, __fsub_rn(a[1], o[1]));
+            const float gz = __fmul_rn(g, __fsub_rn(a[2], o[2]));
+            if (phase == 0) {
+                own[0] = gx; own[1] = gy; own[2] = gz;
+            } else {
+                float *oth = acc + (side ? 0 : n1 * 3) + j2 * 3;
+                atomicAdd(oth + 0, -gx); atomicAdd(oth + 1, -gy); atomicAdd(oth + 2, -gz);
+            }
+        }
+        if (phase == 0) __syncthreads();
     }
     __syncthreads();
     float *g1 = p.grad[0] + b * n1 * 3, *g2 = p.grad[1] + b * n2 * 3;

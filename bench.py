@@ -93,7 +93,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.002)
 
     def start(self):
         if self.ok:
@@ -209,12 +209,18 @@ def run_retrieval(args):
     out_i = torch.empty(Q, k, dtype=torch.int32).pin_memory()
     pairs_per_step = 2.0 * Q * S * n * n
 
+    # one rank: CUDA-graph engine by default; several ranks: eager scoring + one all_gather (measured faster at 8 GPUs
+    # for single-query steps), graph incl. the collective on request
+    use_graph = (not args.eager) and (world == 1 or args.graph)
+    args.eager = not use_graph
+    engine = ured.RetrievalEngine(shard, lo, Q, k=k, metric="cd_t", use_graph=use_graph)
+
     def step_device():
-        return ured.retrieve_sharded(tg_dev, shard, lo, k=k, metric="cd_t")
+        return engine.query(tg_dev)
 
     def step_e2e():
         t = tg_pin.to(dev, non_blocking=True)
-        v, i = ured.retrieve_sharded(t, shard, lo, k=k, metric="cd_t")
+        v, i = engine.query(t)
         out_s.copy_(v, non_blocking=True)
         out_i.copy_(i, non_blocking=True)
 
@@ -254,11 +260,12 @@ def run_retrieval(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "library_shapes": S, "queries": Q, "points": n, "top_k": k,
-                   "shard": [lo, hi], "collective": "one all_gather of [Q,k] (score,id) pairs per step" if world > 1 else "none (1 rank)",
+                   "shard": [lo, hi], "engine": "eager" if args.eager else ("cuda-graph" + ("" if world == 1 else " incl. all_gather")),
+                   "collective": "one all_gather of [Q,k] (score,id) pairs per step" if world > 1 else "none (1 rank)",
                    "l2": "library shard (%.0f MB packed + raw) exceeds L2 except at the smallest sizes" % ((hi - lo) * n * 28 / 1e6)},
         "e2e": {"value": pairs_per_step / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(tg_pin.numel() * 4), "d2h_bytes_per_step": int(Q * k * 8)},
-        "gpu_launches": int(launches), "clocks": sampler.summary(),
+        "gpu_launches": int(launches) if args.eager else int(engine.kernels_per_replay * args.steps), "clocks": sampler.summary(),
         "top1": {"score": float(v[0, 0]), "id": int(i[0, 0])},
     }
     if rank == 0:
@@ -278,6 +285,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + sorted(RETRIEVAL))
     ap.add_argument("--library-size", type=int, default=0, help="override S for the retrieval workloads")
     ap.add_argument("--queries", type=int, default=0, help="override Q for the retrieval workloads")
+    ap.add_argument("--eager", action="store_true", help="retrieval workloads: eager calls instead of the CUDA-graph engine")
+    ap.add_argument("--graph", action="store_true", help="retrieval workloads on >1 rank: capture scoring + all_gather + merge in one CUDA graph")
     ap.add_argument("--exact-only", action="store_true", help="disable the screening pass (difference form on every pair)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

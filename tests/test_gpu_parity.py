@@ -392,3 +392,19 @@ def test_all_pairs_and_pickle_layout(ured, oracle, tmp_path):
         got = ured.topk_smallest(dev(torch.tensor(rec["cd_m"], dtype=torch.float32)), k)[1]
         assert got.cpu().tolist() == want.tolist()
     assert (sc[:, 5, :5] == 0).all()
+
+
+def test_retrieval_engine_graph_matches_eager(ured):
+    S, M, Q, k = 40, 256, 3, 10
+    libr = dev(make_clouds(150, S, M, "S"))
+    want_v, want_i = ured.retrieve(dev(make_clouds(151, Q, 300, "S")), libr, k=k)
+    eng = ured.RetrievalEngine(libr, 0, Q, k=k)
+    for seed in (151, 152, 151):  # replay with new inputs, then the first again
+        tg = dev(make_clouds(seed, Q, 300, "S"))
+        v, i = eng.query(tg)
+        ev, ei = ured.retrieve(tg, libr, k=k)
+        assert torch.equal(i, ei) and torch.equal(v, ev)
+    assert torch.equal(i, want_i) and torch.equal(v, want_v)
+    small = ured.RetrievalEngine(libr[:4], 100, Q, k=k, use_graph=False)  # shard shorter than k: padded
+    v, i = small.query(dev(make_clouds(151, Q, 300, "S")))
+    assert (i[:, 4:] == -1).all() and (i[:, :4] >= 100).all() and torch.isinf(v[:, 4:]).all()
