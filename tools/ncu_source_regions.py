@@ -7,8 +7,16 @@ import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 hdr_idx = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
-hi = hdr_idx[0]
-end = hdr_idx[1] - 1 if len(hdr_idx) > 1 else len(rows)
+want = sys.argv[3] if len(sys.argv) > 3 else None   # optional kernel-name substring
+sel = 0
+if want:
+    for n, i in enumerate(hdr_idx):
+        if want in ' '.join(rows[i - 1]):
+            sel = n
+            break
+hi = hdr_idx[sel]
+end = hdr_idx[sel + 1] - 1 if len(hdr_idx) > sel + 1 else len(rows)
+print('kernel:', ' '.join(rows[hi - 1])[:120])
 hdr = rows[hi]
 data = [r for r in rows[hi + 1:end] if len(r) == len(hdr)]
 si = hdr.index('Warp Stall Sampling (All Samples)'); ii = hdr.index('Instructions Executed'); so = hdr.index('Source')
