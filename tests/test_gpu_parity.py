@@ -408,3 +408,38 @@ def test_retrieval_engine_graph_matches_eager(ured):
     small = ured.RetrievalEngine(libr[:4], 100, Q, k=k, use_graph=False)  # shard shorter than k: padded
     v, i = small.query(dev(make_clouds(151, Q, 300, "S")))
     assert (i[:, 4:] == -1).all() and (i[:, :4] >= 100).all() and torch.isinf(v[:, 4:]).all()
+
+
+def test_full_size_properties_cfg2(ured):
+    """BASELINE configs[1] at full size (640 pairs of 2048 x 2048): properties that need no CPU oracle."""
+    B, N = 640, 2048
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(B, N, 3, generator=g); x = (x - x.mean(1, keepdim=True)); x = (x / x.norm(dim=2).amax(1).view(B, 1, 1)).cuda()
+    y = (x[torch.randperm(B, generator=g)] * 0.97 + 0.01 * torch.randn(B, N, 3, generator=g).cuda()).contiguous()
+    d1, d2, i1, i2 = ured.nn_forward(x, y)
+    # (1) the two kernels agree bit for bit
+    e = ured.nn_forward(x, y, exact_only=True)
+    assert all(torch.equal(a, b) for a, b in zip((d1, d2, i1, i2), e))
+    # (2) swapping the clouds swaps the outputs (the squared difference is exactly antisymmetric-invariant)
+    s1, s2, j1, j2 = ured.nn_forward(y, x)
+    assert torch.equal(s1, d2) and torch.equal(s2, d1) and torch.equal(j1, i2) and torch.equal(j2, i1)
+    # (3) the reported distance is the distance to the reported neighbour (same difference form, fp32 round-off only)
+    nb = torch.gather(y, 1, i1.long().unsqueeze(-1).expand(-1, -1, 3))
+    chk = ((nb - x) ** 2).sum(-1)
+    assert torch.allclose(chk, d1, rtol=1e-5, atol=1e-12)
+    # (4) optimality on a sample of queries against a float64 brute force
+    qs = torch.randint(0, N, (64,), generator=g).cuda()
+    for b in (0, 319, 639):
+        full = ((x[b, qs].double().unsqueeze(1) - y[b].double().unsqueeze(0)) ** 2).sum(-1)
+        assert torch.allclose(full.min(1).values.float(), d1[b, qs], rtol=1e-5, atol=1e-12)
+    # (5) permuting the candidates permutes the indices and leaves the distances untouched
+    perm = torch.randperm(N, generator=g).cuda()
+    p1, _, k1, _ = ured.nn_forward(x[:8], y[:8, perm].contiguous())
+    assert torch.equal(p1, d1[:8])
+    same = perm[k1.long()] == i1[:8]
+    tie_ok = torch.gather(y[:8], 1, perm[k1.long()].unsqueeze(-1).expand(-1, -1, 3))
+    assert torch.allclose(((tie_ok - x[:8]) ** 2).sum(-1)[~same], chk[:8][~same], rtol=1e-6, atol=0)  # differing picks are ties
+    # (6) idempotence of the DCD scores and rankings across repeated calls (deterministic forward)
+    a = ured.calc_dcd(y, x)
+    b2 = ured.calc_dcd(y, x)
+    assert all(torch.equal(u, v) for u, v in zip(a, b2))
