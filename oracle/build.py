@@ -28,6 +28,18 @@ def build_oracle(force=False):
     return ORACLE_SO
 
 
+SCREEN_SO = os.path.join(HERE, "libscreen_model.so")
+
+
+def build_screen_model(force=False):
+    """gcc oracle/screen_model.c -> oracle/libscreen_model.so (CPU emulation of the screening invariant)."""
+    src = os.path.join(HERE, "screen_model.c")
+    if not force and os.path.exists(SCREEN_SO) and os.path.getmtime(SCREEN_SO) >= os.path.getmtime(src):
+        return SCREEN_SO
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", SCREEN_SO, src, "-lm"], check=True)
+    return SCREEN_SO
+
+
 def ref_module_path():
     if not os.path.isdir(REF_DIR):
         return None
