@@ -152,6 +152,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  : "memory");
 }
 
+// 256-bit read-only global load (sm_100: LDG.E.256): one full 32-byte sector per lane and request
+struct __align__(32) float8 { float v[8]; };
+__device__ __forceinline__ float8 ldg256(const float *p) {
+    float8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------
 // nearest-neighbour kernel
 // ------------------------------------------------------------------------------------------
@@ -355,19 +365,18 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
         float bd = 0.0f;
         int bi = c;
 #pragma unroll
-        for (int k = 0; k < G; k += 4) {
-            const float4 x4 = *reinterpret_cast<const float4 *>(gX + c + k);
-            const float4 y4 = *reinterpret_cast<const float4 *>(gY + c + k);
-            const float4 z4 = *reinterpret_cast<const float4 *>(gZ + c + k);
-            const float2 dx0 = __fadd2_rn(make_float2(x4.x, x4.y), nqx), dx1 = __fadd2_rn(make_float2(x4.z, x4.w), nqx);
-            const float2 dy0 = __fadd2_rn(make_float2(y4.x, y4.y), nqy), dy1 = __fadd2_rn(make_float2(y4.z, y4.w), nqy);
-            const float2 dz0 = __fadd2_rn(make_float2(z4.x, z4.y), nqz), dz1 = __fadd2_rn(make_float2(z4.z, z4.w), nqz);
-            const float2 d01 = __ffma2_rn(dz0, dz0, __ffma2_rn(dx0, dx0, __fmul2_rn(dy0, dy0)));
-            const float2 d23 = __ffma2_rn(dz1, dz1, __ffma2_rn(dx1, dx1, __fmul2_rn(dy1, dy1)));
-            if (k == 0 || d01.x < bd) { bd = d01.x; bi = c + k; }   // strict '<' in ascending order: lowest index wins
-            if (d01.y < bd) { bd = d01.y; bi = c + k + 1; }
-            if (d23.x < bd) { bd = d23.x; bi = c + k + 2; }
-            if (d23.y < bd) { bd = d23.y; bi = c + k + 3; }
+        for (int k = 0; k < G; k += 8) {
+            // per-lane scattered reads of the chunk: 256-bit loads fetch each 32-byte sector exactly once
+            const float8 x8 = ldg256(gX + c + k), y8 = ldg256(gY + c + k), z8 = ldg256(gZ + c + k);
+#pragma unroll
+            for (int h = 0; h < 8; h += 2) {
+                const float2 dx = __fadd2_rn(make_float2(x8.v[h], x8.v[h + 1]), nqx);
+                const float2 dy = __fadd2_rn(make_float2(y8.v[h], y8.v[h + 1]), nqy);
+                const float2 dz = __fadd2_rn(make_float2(z8.v[h], z8.v[h + 1]), nqz);
+                const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+                if ((k == 0 && h == 0) || d.x < bd) { bd = d.x; bi = c + k + h; }  // strict '<' in ascending order: lowest index wins
+                if (d.y < bd) { bd = d.y; bi = c + k + h + 1; }
+            }
         }
         if (SCREEN) {
             // |s + |q|^2 - d_fp32| <= 11.02 u S^2 with S = |q| + max|c| (DESIGN.md "screening bound");

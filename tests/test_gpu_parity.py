@@ -443,3 +443,48 @@ def test_full_size_properties_cfg2(ured):
     a = ured.calc_dcd(y, x)
     b2 = ured.calc_dcd(y, x)
     assert all(torch.equal(u, v) for u, v in zip(a, b2))
+
+
+def test_backward_general_path_large_pairs(ured, oracle):
+    """Pairs above 8192 points take grad_kernel<own/scatter> (global atomics) instead of grad_smem_kernel; also ragged."""
+    B, N, M = 2, 6000, 5000
+    a, b = make_clouds(160, B, N, "S"), make_clouds(161, B, M, "S")
+    g = torch.Generator().manual_seed(4)
+    w1, w2 = torch.randn(B, N, generator=g), torch.randn(B, M, generator=g)
+    xa, xb = dev(a).requires_grad_(), dev(b).requires_grad_()
+    d1, d2, i1, i2 = ured.chamfer_3DDist()(xa, xb)
+    ((d1 * dev(w1)).sum() + (d2 * dev(w2)).sum()).backward()
+    o = oracle.c.chamfer_forward(a.numpy(), b.numpy())
+    assert np.array_equal(i1.cpu().numpy(), o[2]) and np.array_equal(i2.cpu().numpy(), o[3])
+    r1, r2 = oracle.c.chamfer_backward_f64(a.numpy(), b.numpy(), w1.numpy(), w2.numpy(), o[2], o[3])
+    assert rel_err(xa.grad.cpu().numpy(), r1) < RTOL and rel_err(xb.grad.cpu().numpy(), r2) < RTOL
+    # ragged lengths on the same path, DCD loss
+    len_x, len_gt = torch.tensor([4500, 5000], dtype=torch.int32), torch.tensor([6000, 3333], dtype=torch.int32)
+    x, gt = dev(b).requires_grad_(), dev(a).requires_grad_()
+    loss = ured.chamfer_ragged(x, gt, dev(len_x), dev(len_gt), alpha=200, n_lambda=0.5)[0]
+    loss.sum().backward()
+    for s in range(B):
+        lx, lg = int(len_x[s]), int(len_gt[s])
+        xo, gto = b[s:s + 1, :lx].clone().requires_grad_(), a[s:s + 1, :lg].clone().requires_grad_()
+        ol = oracle.t.calc_dcd_oracle(xo, gto, alpha=200, n_lambda=0.5)[0]
+        ol.sum().backward()
+        assert np.isclose(loss[s].item(), ol.item(), rtol=RTOL)
+        assert rel_err(x.grad[s, :lx].cpu().numpy(), xo.grad[0].numpy()) < RTOL
+        assert rel_err(gt.grad[s, :lg].cpu().numpy(), gto.grad[0].numpy()) < RTOL
+        assert (x.grad[s, lx:] == 0).all() and (gt.grad[s, lg:] == 0).all()
+
+
+def test_knn1_with_candidate_splits(ured, oracle):
+    """One-direction search on a shape that is cut into candidate splits (few pairs, large clouds)."""
+    p1, p2 = make_clouds(170, 1, 2048, "S"), make_clouds(171, 1, 4100, "S")
+    lib = ured._native.load()
+    assert lib.ured_nn_scratch_bytes(1, 2048, 4100) > 0
+    dists, idx, nn = ured.knn1_points(dev(p1), dev(p2))
+    d1, _, i1, _ = oracle.c.chamfer_forward(p1.numpy(), p2.numpy())
+    assert np.array_equal(idx[0, :, 0].cpu().numpy(), i1[0].astype(np.int64))
+    assert np.array_equal(dists[0, :, 0].cpu().numpy(), d1[0])
+    assert torch.equal(nn[0, :, 0].cpu(), p2[0][torch.from_numpy(i1[0]).long()])
+    # ragged candidates on the split path
+    dists, idx, _ = ured.knn1_points(dev(p1), dev(p2), lengths2=torch.tensor([3000]))
+    d1, _, i1, _ = oracle.c.chamfer_forward(p1.numpy(), p2[:, :3000].numpy())
+    assert np.array_equal(idx[0, :, 0].cpu().numpy(), i1[0].astype(np.int64)) and np.array_equal(dists[0, :, 0].cpu().numpy(), d1[0])
