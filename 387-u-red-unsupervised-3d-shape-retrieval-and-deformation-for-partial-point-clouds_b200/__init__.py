@@ -16,6 +16,7 @@ from .dist_chamfer_3D import chamfer_3DDist as cd
 from .model_utils import calc_cd, calc_dcd, chamfer_ragged, fscore
 from .chamfer_loss import ChamferLoss, chamfer_distance2, compute_cm_loss
 from . import retrieval
+from . import compat
 from .knn import knn1_points, residual_retrieval_loss
 from .retrieval import (RetrievalEngine, PackedClouds, score_all_pairs, write_pair_pickles, score_candidates, score_library, topk_smallest, retrieve,
                         retrieve_sharded, shard_bounds, merge_topk, gather_and_merge)

@@ -1,0 +1,46 @@
+"""CPU: the alias modules let the REFERENCE's own caller files import unmodified (only where /root/reference exists)."""
+import importlib.util
+import os
+import sys
+
+import pytest
+
+REF = "/root/reference"
+
+
+@pytest.fixture()
+def installed(ured):
+    before = dict(sys.modules)
+    names = ured.compat.install()
+    yield ured, names
+    for n in list(sys.modules):
+        if n not in before:
+            del sys.modules[n]
+
+
+def test_aliases_resolve_to_this_package(installed):
+    ured, names = installed
+    assert "Shape_Measure.distance" in names and "Density_aware_Chamfer_Distance.utils_v2.model_utils" in names
+    from Density_aware_Chamfer_Distance.utils_v2.metrics import cd, fscore
+    from Density_aware_Chamfer_Distance.utils_v2.model_utils import calc_cd, calc_dcd, calc_emd
+    from Shape_Measure.distance import ChamferLoss, EMDLoss
+    assert cd is ured.chamfer_3DDist and calc_dcd is ured.calc_dcd and calc_cd is ured.calc_cd and fscore is ured.fscore
+    assert ChamferLoss is ured.ChamferLoss
+    with pytest.raises(NotImplementedError):
+        calc_emd(None, None)
+    with pytest.raises(NotImplementedError):
+        EMDLoss()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the authoring container")
+def test_reference_caller_files_import_unmodified(installed):
+    """loss/chamfer_loss.py of the reference (imports pytorch3d + Shape_Measure, both absent here) loads over the aliases."""
+    ured, _ = installed
+    spec = importlib.util.spec_from_file_location("ref_chamfer_loss", os.path.join(REF, "loss/chamfer_loss.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.ChamferLoss is ured.ChamferLoss
+    assert callable(mod.chamfer_distance2) and callable(mod.compute_cm_loss) and mod.chamfer_distance is ured.compat.chamfer_distance
+    import torch
+    with pytest.raises(RuntimeError, match="GPU tensors only"):   # the reference's code reaches our op (no CPU fallback)
+        mod.chamfer_distance2(torch.rand(1, 8, 3), torch.rand(1, 8, 3))

@@ -488,3 +488,19 @@ def test_knn1_with_candidate_splits(ured, oracle):
     dists, idx, _ = ured.knn1_points(dev(p1), dev(p2), lengths2=torch.tensor([3000]))
     d1, _, i1, _ = oracle.c.chamfer_forward(p1.numpy(), p2[:, :3000].numpy())
     assert np.array_equal(idx[0, :, 0].cpu().numpy(), i1[0].astype(np.int64)) and np.array_equal(dists[0, :, 0].cpu().numpy(), d1[0])
+
+
+def test_compat_pytorch3d_subset(ured, oracle):
+    """The pytorch3d-shaped entry points the reference calls (loss/chamfer_loss.py:1, loss/basic_loss.py:257)."""
+    x0, y0 = make_clouds(180, 3, 500, "S"), make_clouds(181, 3, 640, "S")
+    d1, d2, i1, _ = oracle.c.chamfer_forward(x0.numpy(), y0.numpy())
+    per_sample = d1.astype(np.float64).mean(1) + d2.astype(np.float64).mean(1)
+    loss, normals = ured.compat.chamfer_distance(dev(x0), dev(y0), batch_reduction=None)
+    assert normals is None and np.allclose(loss.cpu().numpy(), per_sample, rtol=RTOL)
+    loss, _ = ured.compat.chamfer_distance(dev(x0), dev(y0))
+    assert np.isclose(loss.item(), per_sample.mean(), rtol=RTOL)
+    knn = ured.compat.knn_points(dev(x0), dev(y0), K=1, return_nn=True)
+    assert knn.dists.shape == (3, 500, 1) and knn.idx.dtype == torch.int64 and knn.knn.shape == (3, 500, 1, 3)
+    assert np.array_equal(knn.idx[..., 0].cpu().numpy(), i1.astype(np.int64))
+    with pytest.raises(NotImplementedError):
+        ured.compat.knn_points(dev(x0), dev(y0), K=3)
