@@ -151,7 +151,7 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return
     B, n_x, n_gt, desc = WORKLOADS[wl]
-    sample_pairs = 32 if n_x * n_gt <= 2048 * 2048 else 1
+    sample_pairs = int(os.environ.get("URED_BENCH_CPU_SAMPLE", "0")) or (32 if n_x * n_gt <= 2048 * 2048 else 1)
     steps = max(1, min(args.steps, 5))       # bounded: each step is ~1-3 s of CPU work on 8-16 cores
     warmup = max(1, min(args.warmup, 1))
     base = cpu_baseline(n_x, n_gt, sample_pairs, steps, warmup)
