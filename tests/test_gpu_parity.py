@@ -93,6 +93,21 @@ def test_golden_reference_python(ured):
         assert np.array_equal(i1, g[f"{case}_idx1"]) and np.array_equal(i2, g[f"{case}_idx2"])
 
 
+def test_golden_reference_cuda_op(ured):
+    """Against the committed outputs of the unmodified reference CUDA op on a B200 (make_golden_gpu.py): bits for dist/idx."""
+    g = np.load(os.path.join(GOLD, "chamfer_ref_cuda_b200.npz"))
+    for case in ["unit_test", "timing", "ragged_tail", "lattice", "chair"]:
+        for exact_only in (False, True):
+            got = run_fwd(ured, torch.from_numpy(g[f"{case}_xyz1"]), torch.from_numpy(g[f"{case}_xyz2"]), exact_only)
+            assert_bit_exact(got, [g[f"{case}_dist1"], g[f"{case}_dist2"], g[f"{case}_idx1"], g[f"{case}_idx2"]], case)
+        xa = dev(torch.from_numpy(g[f"{case}_xyz1"])).requires_grad_()
+        xb = dev(torch.from_numpy(g[f"{case}_xyz2"])).requires_grad_()
+        d1, d2, _, _ = ured.chamfer_3DDist()(xa, xb)
+        ((d1 * dev(torch.from_numpy(g[f"{case}_w1"]))).sum() + (d2 * dev(torch.from_numpy(g[f"{case}_w2"]))).sum()).backward()
+        for got, want in [(xa.grad, g[f"{case}_grad1"]), (xb.grad, g[f"{case}_grad2"])]:
+            assert np.abs(got.cpu().numpy() - want).max() / (np.abs(want).max() + 1e-30) < RTOL
+
+
 def rel_err(got, want):
     scale = np.abs(want).max() + 1e-30
     return np.abs(got - want).max() / scale

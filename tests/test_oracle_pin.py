@@ -84,3 +84,21 @@ def test_oracle_backward_matches_autograd_of_python_chamfer(oracle):
     assert np.allclose(g2, b64.grad.numpy(), rtol=1e-4, atol=1e-6)
     h1, h2 = oracle.c.chamfer_backward_f64(a.numpy(), b.numpy(), w1.numpy(), w2.numpy(), i1, i2)
     assert np.allclose(g1, h1, rtol=1e-5, atol=1e-7) and np.allclose(g2, h2, rtol=1e-5, atol=1e-7)
+
+
+CUDA_CASES = ["unit_test", "timing", "ragged_tail", "lattice", "chair"]
+
+
+@pytest.mark.parametrize("case", CUDA_CASES)
+def test_oracle_bit_exact_vs_reference_cuda_op_golden(oracle, case):
+    """tests/golden/chamfer_ref_cuda_b200.npz holds outputs of the UNMODIFIED reference CUDA op run on a B200
+    (tests/golden/make_golden_gpu.py): the C oracle must reproduce dist/idx bit for bit, gradients to 1e-5."""
+    g = np.load(os.path.join(GOLD, "chamfer_ref_cuda_b200.npz"))
+    a, b = g[f"{case}_xyz1"], g[f"{case}_xyz2"]
+    d1, d2, i1, i2 = oracle.c.chamfer_forward(a, b)
+    assert np.array_equal(d1.view(np.uint32), g[f"{case}_dist1"].view(np.uint32))
+    assert np.array_equal(d2.view(np.uint32), g[f"{case}_dist2"].view(np.uint32))
+    assert np.array_equal(i1, g[f"{case}_idx1"]) and np.array_equal(i2, g[f"{case}_idx2"])
+    r1, r2 = oracle.c.chamfer_backward_f64(a, b, g[f"{case}_w1"], g[f"{case}_w2"], i1, i2)
+    for got, want in [(g[f"{case}_grad1"], r1), (g[f"{case}_grad2"], r2)]:
+        assert np.abs(got - want).max() / (np.abs(want).max() + 1e-30) < 1e-5
