@@ -467,6 +467,7 @@ def main():
                      "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops, "traffic": traffic,
                      "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 FLOP x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz; it has no FP32 figure); "
                                     "tools/microbench/fp32_peak.cu measured 72.6 (FFMA) / 74.3 (FFMA2) TFLOP/s on this pool",
+                     "frac_of_measured_ffma_peak": achieved_tflops / 72.6,  # profiles/r01_microbench_fp32_peak.txt (scalar FFMA stream)
                      "flop_per_launch": flop_per_launch, "kernel_ms": ms_nn,
                      "tpair_per_s": pairs_per_step / (ms_nn * 1e-3) / 1e12,
                      "note": "FLOP-accounted at the reference's 8 FLOP per ordered pair; the screening variant executes 6 FLOP per pair in its main loop"},
