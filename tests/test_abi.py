@@ -69,3 +69,13 @@ def test_product_never_imports_the_oracle():
             text = open(path).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
             assert "liboracle" not in text, path
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/ured_chamfer.h must be consumable by a C compiler (cgo/JNI/ctypes-style FFI users), not only by nvcc."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "ured_chamfer.h"\n'
+                   'int probe(void) { return ured_abi_version() == URED_ABI_VERSION && URED_E_NULL < 0 && (URED_FLAG_EXACT_ONLY | URED_FLAG_NON_REG | URED_FLAG_ONE_DIRECTION) == 7u; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "use_header.o")],
+                   check=True)
