@@ -17,6 +17,7 @@ from .model_utils import calc_cd, calc_dcd, chamfer_ragged, fscore
 from .chamfer_loss import ChamferLoss, chamfer_distance2, compute_cm_loss
 from . import retrieval
 from . import compat
+from .graphed import GraphedDCD
 from .knn import knn1_points, residual_retrieval_loss
 from .retrieval import (RetrievalEngine, PackedClouds, score_all_pairs, write_pair_pickles, score_candidates, score_library, topk_smallest, retrieve,
                         retrieve_sharded, shard_bounds, merge_topk, gather_and_merge)
@@ -24,7 +25,7 @@ from .retrieval import (RetrievalEngine, PackedClouds, score_all_pairs, write_pa
 __all__ = [
     "chamfer_3DDist", "chamfer_3DFunction", "nn_forward", "nn_backward", "cd", "fscore", "calc_cd", "calc_dcd", "chamfer_ragged",
     "ChamferLoss", "chamfer_distance2", "compute_cm_loss",
-    "knn1_points", "residual_retrieval_loss", "PackedClouds", "RetrievalEngine", "score_candidates", "score_library", "score_all_pairs", "write_pair_pickles", "topk_smallest", "retrieve",
+    "knn1_points", "residual_retrieval_loss", "PackedClouds", "RetrievalEngine", "GraphedDCD", "score_candidates", "score_library", "score_all_pairs", "write_pair_pickles", "topk_smallest", "retrieve",
     "retrieve_sharded", "shard_bounds", "merge_topk", "gather_and_merge",
     "NativeLibraryError", "build_native",
 ]
