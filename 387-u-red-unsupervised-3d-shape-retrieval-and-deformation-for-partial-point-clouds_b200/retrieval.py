@@ -313,7 +313,12 @@ class RetrievalEngine:
     def __init__(self, local_library, shard_offset, num_queries, k=10, metric="cd_t", alpha=1000, n_lambda=1,
                  group=None, use_graph=True, max_pairs=16384):
         graph_collective = True
-        self.lib = _as_packed(local_library) if local_library is not None and len(local_library.xyz if isinstance(local_library, PackedClouds) else local_library) else None
+        if local_library is None:
+            self.lib = None
+        elif isinstance(local_library, PackedClouds):
+            self.lib = local_library if local_library.count else None
+        else:
+            self.lib = PackedClouds(local_library) if len(local_library) else None  # an empty shard holds nothing
         self.offset, self.Q, self.k, self.metric = int(shard_offset), int(num_queries), int(k), metric
         self.alpha, self.n_lambda, self.group, self.max_pairs = alpha, n_lambda, group, max_pairs
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
