@@ -79,3 +79,22 @@ def test_header_is_plain_c(tmp_path):
                    'int probe(void) { return ured_abi_version() == URED_ABI_VERSION && URED_E_NULL < 0 && (URED_FLAG_EXACT_ONLY | URED_FLAG_NON_REG | URED_FLAG_ONE_DIRECTION) == 7u; }\n')
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "use_header.o")],
                    check=True)
+
+
+def test_launch_shape_heuristic_invariants(ured):
+    """ured_nn_scratch_bytes exposes the candidate-split choice: 1, 2, 4 or 8 splits, never below 512 candidates per split,
+    none when the grid is already large, and the workspace formula stays consistent with it."""
+    lib = ured._native.load()
+    for B in [1, 2, 7, 16, 32, 100, 640, 5000]:
+        for n1, n2 in [(1, 1), (100, 200), (511, 4096), (1024, 1024), (2048, 2048), (2000, 1000), (16384, 16384), (4096, 100000)]:
+            sb = lib.ured_nn_scratch_bytes(B, n1, n2)
+            per_split = B * (n1 + n2) * 8
+            nsplit = 1 if sb == 0 else -(-sb // per_split) if sb % per_split else sb // per_split
+            if sb:
+                assert sb % 256 == 0 and nsplit in (2, 4, 8) and sb - nsplit * per_split < 256
+                assert min(n1, n2) // nsplit >= 512                       # a split never gets fewer than 512 candidates
+            q4 = B * (-(-n1 // 512) + -(-n2 // 512))
+            if q4 >= 148 * 6 * 4:
+                assert sb == 0                                            # enough CTAs already: no splitting
+            assert lib.ured_chamfer_workspace_bytes(B, n1, n2) == lib.ured_packed_bytes(B, n1) + lib.ured_packed_bytes(B, n2) + sb
+    assert lib.ured_nn_scratch_bytes(0, 8, 8) == 0 and lib.ured_nn_scratch_bytes(4, 0, 8) == 0
