@@ -34,14 +34,25 @@ _SIGNATURES = {
     "ured_packed_bytes": (_sz, [_i, _i]),
     "ured_pack_clouds": (_i, [_p, _i, _i, _p, _p, _p]),
     "ured_nn_scratch_bytes": (_sz, [_i, _i, _i]),
+    "ured_nn_launch_shape": (_i, [_i, _i, _i, _u, _p, _p, _p, _p]),
     "ured_nn_packed": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _u, _p]),
     "ured_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
     "ured_chamfer_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _u, _p]),
     "ured_chamfer_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ured_dcd_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _f, _f, _f, _f, _u, _p, _p, _p, _p, _p, _p]),
+    "ured_dcd_forward_ex": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _f, _f, _f, _f, _u, _p, _p, _p, _p, _p, _p, _f, _p]),
     "ured_dcd_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ured_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "ured_topk_smallest": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "ured_probe_ffma": (_i, [_p, _i, _i, ctypes.POINTER(ctypes.c_double), _p]),
+    "ured_xchg_bytes": (_sz, [_i, _i, _i]),
+    "ured_xchg_alloc": (_i, [_sz, ctypes.POINTER(ctypes.c_void_p)]),
+    "ured_xchg_free": (_i, [_p]),
+    "ured_xchg_export": (_i, [_p, _p]),
+    "ured_xchg_import": (_i, [_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "ured_xchg_close": (_i, [_p]),
+    "ured_xchg_status": (_i, [_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint), _p]),
+    "ured_topk_exchange": (_i, [_p, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _i, _i, _i, _p, _p, _u, _p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

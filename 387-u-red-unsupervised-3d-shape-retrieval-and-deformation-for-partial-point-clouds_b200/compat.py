@@ -10,9 +10,15 @@
     # resolve to this package.
 
 Only names on the Chamfer hot path are provided.  `emd` / `EMDLoss` / `calc_emd` (the auction EMD op, out of scope) are
-placeholders that raise when CALLED, so importing modules that merely mention them keeps working.  A module that is
-really installed (e.g. a genuine pytorch3d) is never replaced unless ``force=True``.
+placeholders that raise when CALLED, so importing modules that merely mention them keeps working.
+
+`Density_aware_Chamfer_Distance.*` and `Shape_Measure.*` are ALWAYS aliased: they are exactly what this package
+replaces, and with the reference root on sys.path (the documented flow) the genuine DCD package is importable -- leaving
+it in place would silently JIT-build and run the reference's CUDA op.  The alias packages keep the genuine package's
+search path, so its other submodules (models, cfgs, ...) still import from disk.  Only a genuinely installed
+`pytorch3d` is left alone unless ``force=True`` (a warning says so).
 """
+import warnings
 import importlib.util
 import sys
 import types
@@ -100,13 +106,29 @@ def install(force=False):
         "pytorch3d.ops": dict(knn_points=knn_points),
     }
     done = []
+    keep_genuine = set()
+    if not force and _really_installed("pytorch3d"):
+        keep_genuine.add("pytorch3d")
+        warnings.warn("ured_b200.compat.install(): a genuine pytorch3d is installed and is left in place; pass force=True to route "
+                      "pytorch3d.loss.chamfer_distance / pytorch3d.ops.knn_points to the B200 path", stacklevel=2)
     for name, attrs in mods.items():
         top = name.split(".")[0]
-        if not force and _really_installed(top) and not getattr(sys.modules.get(top), "__ured_b200_compat__", False):
-            continue  # a genuine package of that name exists: leave it alone
+        if top in keep_genuine:
+            continue
         mod = _module(name, **attrs)
         if attrs == {}:
-            mod.__path__ = []  # package
+            # package: keep the genuine package's search path (if there is one) for the submodules we do not alias
+            path = []
+            if not getattr(sys.modules.get(name), "__ured_b200_compat__", False):
+                try:
+                    spec = importlib.util.find_spec(name) if name not in sys.modules else getattr(sys.modules[name], "__spec__", None)
+                    if spec is not None and spec.submodule_search_locations:
+                        path = list(spec.submodule_search_locations)
+                except (ImportError, ValueError, AttributeError):
+                    path = []
+            else:
+                path = list(getattr(sys.modules[name], "__path__", []))
+            mod.__path__ = path
         sys.modules[name] = mod
         parent, _, child = name.rpartition(".")
         if parent and parent in sys.modules:

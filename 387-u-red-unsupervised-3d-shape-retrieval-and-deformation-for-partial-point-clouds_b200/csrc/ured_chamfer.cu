@@ -28,6 +28,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include <atomic>
@@ -165,7 +166,6 @@ __device__ __forceinline__ float8 ldg256(const float *p) {
 // ------------------------------------------------------------------------------------------
 // nearest-neighbour kernel
 // ------------------------------------------------------------------------------------------
-constexpr int kNNThreads = 128;  // 4 warps, one per SM sub-partition; 5-6 CTAs resident per SM
 constexpr int kTile = 1024;      // candidates per shared-memory stage (768 was tried: 7 CTAs/SM but 3% slower on cfg2)
 constexpr int kStages = 2;
 constexpr int kChunk = 32;       // candidates per running-minimum chunk (= the padding granule of the packed image)
@@ -196,10 +196,14 @@ __device__ __forceinline__ float exact_d(float cx, float cy, float cz, float qx,
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
-template <bool SCREEN, int R>
-__global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
+// Launch variants: T threads per CTA, R queries per thread in registers, MINB resident CTAs per SM (register cap).
+// Few fat warps win on this loop: the FFMA2 stream needs no latency hiding beyond its own ILP, a larger R divides the
+// LDS and chunk-bookkeeping instructions per pair, and a looser register cap lets ptxas keep the half-major order.
+template <bool SCREEN, int R, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) nn_kernel(const NNParams p) {
     constexpr int NARR = SCREEN ? 4 : 3;
     constexpr int G = kChunk;
+    constexpr int QT = R * T;  // queries per CTA
     extern __shared__ __align__(128) float stage_mem[];  // kStages * NARR * kTile floats
     __shared__ __align__(8) uint64_t full_bar[kStages];
 
@@ -228,11 +232,11 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
                                  : (dir ? p.part_dist[1] : p.part_dist[0]) + ((size_t)sp * p.B + b) * nq;
     int *out_i = p.nsplit == 1 ? (dir ? p.idx[1] : p.idx[0]) + (size_t)b * nq
                                : (dir ? p.part_idx[1] : p.part_idx[0]) + ((size_t)sp * p.B + b) * nq;
-    if (qt * R * kNNThreads >= nq_v || nc == 0) {
+    if (qt * QT >= nq_v || nc == 0) {
         // nothing to search: the reference kernel leaves its zero-filled outputs untouched in this case
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const int j = (qt * R + r) * kNNThreads + tid;
+            const int j = (qt * R + r) * T + tid;
             if (j < nq) { out_d[j] = 0.0f; out_i[j] = 0; }
         }
         return;
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
     constexpr float kScale = SCREEN ? -2.0f : -1.0f, kUnscale = SCREEN ? -0.5f : -1.0f;
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        int j = (qt * R + r) * kNNThreads + tid;
+        int j = (qt * R + r) * T + tid;
         j = j < nq_v ? j : nq_v - 1;
         qx[r] = kScale * qxyz[j * 3 + 0]; qy[r] = kScale * qxyz[j * 3 + 1]; qz[r] = kScale * qxyz[j * 3 + 2];
         best[r] = kInf; second[r] = kInf; bchunk[r] = k_lo;
@@ -301,35 +305,43 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
                 const float4 x4 = *reinterpret_cast<const float4 *>(X + c0 + k);
                 const float4 y4 = *reinterpret_cast<const float4 *>(Y + c0 + k);
                 const float4 z4 = *reinterpret_cast<const float4 *>(Z + c0 + k);
-                if (SCREEN) {
-                    const float4 w4 = *reinterpret_cast<const float4 *>(W + c0 + k);
+                float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (SCREEN) w4 = *reinterpret_cast<const float4 *>(W + c0 + k);
+                // half-major order: one candidate pair against all R queries, layer by layer, so that the 64-bit
+                // candidate operand stays in the operand-reuse slot and only q (1 word) + t (2 words) are read per FFMA2
 #pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        const float2 bx = make_float2(qx[r], qx[r]), by = make_float2(qy[r], qy[r]), bz = make_float2(qz[r], qz[r]);
-                        float2 t0 = __ffma2_rn(make_float2(z4.x, z4.y), bz, make_float2(w4.x, w4.y));
-                        float2 t1 = __ffma2_rn(make_float2(z4.z, z4.w), bz, make_float2(w4.z, w4.w));
-                        t0 = __ffma2_rn(make_float2(y4.x, y4.y), by, t0);
-                        t1 = __ffma2_rn(make_float2(y4.z, y4.w), by, t1);
-                        t0 = __ffma2_rn(make_float2(x4.x, x4.y), bx, t0);
-                        t1 = __ffma2_rn(make_float2(x4.z, x4.w), bx, t1);
-                        cm[r] = fminf(fminf(cm[r], t0.x), t0.y);
-                        cm[r] = fminf(fminf(cm[r], t1.x), t1.y);
-                    }
-                } else {
+                for (int h = 0; h < 2; h++) {
+                    const float2 xp = h ? make_float2(x4.z, x4.w) : make_float2(x4.x, x4.y);
+                    const float2 yp = h ? make_float2(y4.z, y4.w) : make_float2(y4.x, y4.y);
+                    const float2 zp = h ? make_float2(z4.z, z4.w) : make_float2(z4.x, z4.y);
+                    float2 tt[R];
+                    if (SCREEN) {
+                        const float2 wp = h ? make_float2(w4.z, w4.w) : make_float2(w4.x, w4.y);
 #pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        const float2 bx = make_float2(qx[r], qx[r]), by = make_float2(qy[r], qy[r]), bz = make_float2(qz[r], qz[r]);
-                        const float2 dx0 = __fadd2_rn(make_float2(x4.x, x4.y), bx), dx1 = __fadd2_rn(make_float2(x4.z, x4.w), bx);
-                        const float2 dy0 = __fadd2_rn(make_float2(y4.x, y4.y), by), dy1 = __fadd2_rn(make_float2(y4.z, y4.w), by);
-                        const float2 dz0 = __fadd2_rn(make_float2(z4.x, z4.y), bz), dz1 = __fadd2_rn(make_float2(z4.z, z4.w), bz);
-                        float2 t0 = __fmul2_rn(dy0, dy0), t1 = __fmul2_rn(dy1, dy1);
-                        t0 = __ffma2_rn(dx0, dx0, t0);
-                        t1 = __ffma2_rn(dx1, dx1, t1);
-                        t0 = __ffma2_rn(dz0, dz0, t0);
-                        t1 = __ffma2_rn(dz1, dz1, t1);
-                        cm[r] = fminf(fminf(cm[r], t0.x), t0.y);
-                        cm[r] = fminf(fminf(cm[r], t1.x), t1.y);
+                        for (int r = 0; r < R; r++) tt[r] = __ffma2_rn(zp, make_float2(qz[r], qz[r]), wp);
+#pragma unroll
+                        for (int r = 0; r < R; r++) tt[r] = __ffma2_rn(yp, make_float2(qy[r], qy[r]), tt[r]);
+#pragma unroll
+                        for (int r = 0; r < R; r++) tt[r] = __ffma2_rn(xp, make_float2(qx[r], qx[r]), tt[r]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const float2 dy = __fadd2_rn(yp, make_float2(qy[r], qy[r]));
+                            tt[r] = __fmul2_rn(dy, dy);
+                        }
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const float2 dx = __fadd2_rn(xp, make_float2(qx[r], qx[r]));
+                            tt[r] = __ffma2_rn(dx, dx, tt[r]);
+                        }
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const float2 dz = __fadd2_rn(zp, make_float2(qz[r], qz[r]));
+                            tt[r] = __ffma2_rn(dz, dz, tt[r]);
+                        }
                     }
+#pragma unroll
+                    for (int r = 0; r < R; r++) cm[r] = fminf(fminf(cm[r], tt[r].x), tt[r].y);
                 }
             }
             // chunk bookkeeping: strict '<' in ascending chunk order keeps the FIRST chunk holding the minimum
@@ -349,42 +361,86 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
     }
 
     // ---- exact resolution of the winning chunk ---------------------------------------------
+    // Tiles t >= ntiles - kStages are still resident in shared memory (nothing was issued over them), i.e. candidates
+    // from k_res on; for clouds of up to kStages * kTile = 2048 candidates per split that is the whole range.
+    const int k_res = k_lo + max(0, ntiles - kStages) * kTile;
     const float *__restrict__ gX = csoa, *__restrict__ gY = csoa + ncp_max, *__restrict__ gZ = csoa + 2 * (size_t)ncp_max;
     float cn = 0.0f;
     if (SCREEN) cn = __fsqrt_ru(csoa[(size_t)ncp_max * 4]) * 1.000001f;  // max W of the candidate cloud (block tail)
     const int lane = tid & 31;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const float oqx = kUnscale * qx[r], oqy = kUnscale * qy[r], oqz = kUnscale * qz[r];
-        const int c = min(bchunk[r], ncp - G);  // (an empty trailing split re-reads the last chunk; its result loses every merge)
+    const int rot = lane & 7;  // 16-byte piece this lane starts its chunk at (see below)
+    // One query per iteration, always from element 0 of the register arrays, which are then shifted down by one: the
+    // loop stays rolled (the re-check is ~400 instructions; unrolled R times it would not fit the instruction cache)
+    // without ever indexing a register array dynamically.
+#pragma unroll 1
+    for (int it = 0; it < R; it++) {
+        const float oqx = kUnscale * qx[0], oqy = kUnscale * qy[0], oqz = kUnscale * qz[0];
+        const int c = min(bchunk[0], ncp - G);  // (an empty trailing split re-reads the last chunk; its result loses every merge)
         // Exact difference form on the chunk's G candidates (packed math, same bits as exact_d).  Entries past nc
         // replicate point nc-1, so they can tie with it but sit at higher indices and never win.
         const float nq1 = SCREEN ? 0.5f : 1.0f;  // registers hold -2q (SCREEN) or -q (EXACT); both rescalings are exact
-        const float2 nqx = make_float2(nq1 * qx[r], nq1 * qx[r]), nqy = make_float2(nq1 * qy[r], nq1 * qy[r]),
-                     nqz = make_float2(nq1 * qz[r], nq1 * qz[r]);
-        float bd = 0.0f;
+        const float2 nqx = make_float2(nq1 * qx[0], nq1 * qx[0]), nqy = make_float2(nq1 * qy[0], nq1 * qy[0]),
+                     nqz = make_float2(nq1 * qz[0], nq1 * qz[0]);
+        // d >= +0 for every finite pair, so the running minimum is kept on the float's bit pattern (same order)
+        unsigned bdu = 0u;
         int bi = c;
+        if (c >= k_res) {
+            // From the resident tile.  Every lane reads its own chunk, 16 bytes (one bank group) at a time.  Chunks start on
+            // 128-byte boundaries, so in natural order the 8 lanes of a quarter-warp phase would all hit the same bank
+            // group; lane l therefore starts at piece (l & 7) and wraps around, which makes every phase conflict-free.
+            // Lowest index on ties in that rotated order: the pieces after the wrap hold LOWER indices than anything seen
+            // before it, so at the wrap the running minimum is bumped by one ulp -- a tie from there on wins, and from
+            // then on strict '<' keeps the first (lowest) of the remaining ties.  If nothing after the wrap won, the
+            // bump is undone.
+            const int tt_i = (c - k_lo) / kTile;
+            const float *sX = stage_mem + ((tt_i % kStages) * NARR + 0) * kTile + (c - k_lo - tt_i * kTile);
+            const float *sY = sX + kTile, *sZ = sX + 2 * kTile;
+            unsigned hdu = 0u;
 #pragma unroll
-        for (int k = 0; k < G; k += 8) {
-            // per-lane scattered reads of the chunk: 256-bit loads fetch each 32-byte sector exactly once
-            const float8 x8 = ldg256(gX + c + k), y8 = ldg256(gY + c + k), z8 = ldg256(gZ + c + k);
+            for (int k = 0; k < 8; k++) {
+                const int piece = (k + rot) & 7;
+                if (k > 0 && piece == 0) { hdu = bdu; bdu += 1u; }
+                const float4 x4 = *reinterpret_cast<const float4 *>(sX + piece * 4);
+                const float4 y4 = *reinterpret_cast<const float4 *>(sY + piece * 4);
+                const float4 z4 = *reinterpret_cast<const float4 *>(sZ + piece * 4);
+                const float2 dx0 = __fadd2_rn(make_float2(x4.x, x4.y), nqx), dx1 = __fadd2_rn(make_float2(x4.z, x4.w), nqx);
+                const float2 dy0 = __fadd2_rn(make_float2(y4.x, y4.y), nqy), dy1 = __fadd2_rn(make_float2(y4.z, y4.w), nqy);
+                const float2 dz0 = __fadd2_rn(make_float2(z4.x, z4.y), nqz), dz1 = __fadd2_rn(make_float2(z4.z, z4.w), nqz);
+                const float2 d0 = __ffma2_rn(dz0, dz0, __ffma2_rn(dx0, dx0, __fmul2_rn(dy0, dy0)));
+                const float2 d1 = __ffma2_rn(dz1, dz1, __ffma2_rn(dx1, dx1, __fmul2_rn(dy1, dy1)));
+                const int i0 = c + piece * 4;
+                const unsigned u0 = __float_as_uint(d0.x), u1 = __float_as_uint(d0.y), u2 = __float_as_uint(d1.x), u3 = __float_as_uint(d1.y);
+                if (k == 0 || u0 < bdu) { bdu = u0; bi = i0; }
+                if (u1 < bdu) { bdu = u1; bi = i0 + 1; }
+                if (u2 < bdu) { bdu = u2; bi = i0 + 2; }
+                if (u3 < bdu) { bdu = u3; bi = i0 + 3; }
+            }
+            if (rot != 0 && bi >= c + rot * 4) bdu = hdu;  // the winner predates the wrap: undo the bump
+        } else {
 #pragma unroll
-            for (int h = 0; h < 8; h += 2) {
-                const float2 dx = __fadd2_rn(make_float2(x8.v[h], x8.v[h + 1]), nqx);
-                const float2 dy = __fadd2_rn(make_float2(y8.v[h], y8.v[h + 1]), nqy);
-                const float2 dz = __fadd2_rn(make_float2(z8.v[h], z8.v[h + 1]), nqz);
-                const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
-                if ((k == 0 && h == 0) || d.x < bd) { bd = d.x; bi = c + k + h; }  // strict '<' in ascending order: lowest index wins
-                if (d.y < bd) { bd = d.y; bi = c + k + h + 1; }
+            for (int k = 0; k < G; k += 8) {
+                // per-lane scattered reads of the chunk: 256-bit loads fetch each 32-byte sector exactly once
+                const float8 x8 = ldg256(gX + c + k), y8 = ldg256(gY + c + k), z8 = ldg256(gZ + c + k);
+#pragma unroll
+                for (int h = 0; h < 8; h += 2) {
+                    const float2 dx = __fadd2_rn(make_float2(x8.v[h], x8.v[h + 1]), nqx);
+                    const float2 dy = __fadd2_rn(make_float2(y8.v[h], y8.v[h + 1]), nqy);
+                    const float2 dz = __fadd2_rn(make_float2(z8.v[h], z8.v[h + 1]), nqz);
+                    const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+                    const unsigned u0 = __float_as_uint(d.x), u1 = __float_as_uint(d.y);
+                    if ((k == 0 && h == 0) || u0 < bdu) { bdu = u0; bi = c + k + h; }  // strict '<' in ascending order: lowest index wins
+                    if (u1 < bdu) { bdu = u1; bi = c + k + h + 1; }
+                }
             }
         }
+        float bd = __uint_as_float(bdu);
         if (SCREEN) {
             // |s + |q|^2 - d_fp32| <= 11.02 u S^2 with S = |q| + max|c| (DESIGN.md "screening bound");
             // a runner-up chunk farther than twice that cannot hold the argmin.  eps = 32 u S^2.
             const float qn = __fsqrt_ru(__fmaf_rn(oqz, oqz, __fmaf_rn(oqy, oqy, oqx * oqx))) * 1.000001f;
             const float S = qn + cn;
             const float eps = __fmaf_rn(S * S, 1.9073486e-6f /* 2^-19 */, 1e-35f);
-            const bool ambiguous = !(second[r] > best[r] + eps);
+            const bool ambiguous = !(second[0] > best[0] + eps);
             unsigned todo = __ballot_sync(0xffffffffu, ambiguous);
             while (todo) {
                 const int src = __ffs(todo) - 1;
@@ -407,12 +463,17 @@ __global__ void __launch_bounds__(kNNThreads) nn_kernel(const NNParams p) {
                 if (lane == src) { bd = wd; bi = wi; }
             }
         }
-        const int j = (qt * R + r) * kNNThreads + tid;
+        const int j = (qt * R + it) * T + tid;
         if (j < nq) {
             if (j >= nq_v) { bd = 0.0f; bi = 0; }                          // past the valid length of a ragged cloud
             else if (p.nsplit > 1 && k_lo >= k_hi) bd = kInf;              // empty split: loses every merge
             out_d[j] = bd;
             out_i[j] = bi;
+        }
+#pragma unroll
+        for (int r = 0; r + 1 < R; r++) {
+            qx[r] = qx[r + 1]; qy[r] = qy[r + 1]; qz[r] = qz[r + 1];
+            best[r] = best[r + 1]; second[r] = second[r + 1]; bchunk[r] = bchunk[r + 1];
         }
     }
 }
@@ -433,30 +494,58 @@ __global__ void __launch_bounds__(256) merge_splits_kernel(const float *__restri
     idx[t] = i;
 }
 
-// Launch shape: R queries per thread and nsplit candidate splits, chosen so that the grid has several waves of
-// CTAs (148 SMs x ~6 resident CTAs) without cutting the candidate range below 512 points per CTA.
-struct NNShape { int R; int nsplit; };
-NNShape choose_nn_shape(int B, int n1, int n2) {
-    auto items = [&](int R) {
-        return (long long)B * ((n1 + R * kNNThreads - 1) / (R * kNNThreads) + (n2 + R * kNNThreads - 1) / (R * kNNThreads));
-    };
-    NNShape sh;
-    sh.R = 4;
-    sh.nsplit = 1;
-    const long long want = 148ll * 6 * 4;
-    const int max_split = (n1 < n2 ? n1 : n2) / 512;
-    if (items(4) < want) {
-        long long need = (want + items(4) - 1) / items(4);
-        while (sh.nsplit < need && sh.nsplit * 2 <= max_split && sh.nsplit < 8) sh.nsplit *= 2;
-        if (items(4) * sh.nsplit < 148ll * 4) sh.R = 2;
-    }
+// Launch shape: a kernel variant (T threads x R queries per thread, MINB resident CTAs per SM) and nsplit candidate
+// splits.  Measured on B200 (profiles/r02_sweep_nn*.jsonl: every variant x split count on the BASELINE shapes):
+//   * the 4-query, 128-thread shape wins whenever there are enough query tiles to give every SM two CTAs; fatter
+//     warps (8-16 queries per thread) lose to it in the full kernel although they win in the isolated main loop;
+//   * clouds of more than 2048 candidates are best cut into 2048-candidate ranges: each CTA then keeps its whole range
+//     resident in the two shared-memory stages (exact re-check from shared memory) and the tail of the grid is made of
+//     small items (cfg4: 6.64 -> 7.36 Tpair/s with 8 splits);
+//   * launches that cannot fill the machine take the 256-query shape and are split down to 512 candidates per CTA.
+struct NNVariant { int R, T, minb; };
+constexpr int kNumVariants = 8;
+const NNVariant kVariants[kNumVariants] = {
+    {4, 128, 5},   // 0: default
+    {4, 128, 4},   // 1
+    {8, 128, 3},   // 2
+    {8, 64, 6},    // 3
+    {16, 64, 4},   // 4
+    {2, 128, 6},   // 5: smallest tile (256 queries) for launches that cannot fill the machine otherwise
+    {8, 128, 2},   // 6
+    {4, 64, 8},    // 7
+};
+constexpr int kDefaultVariant = 0, kSmallVariant = 5;
+struct NNShape { int variant; int R, T; int nsplit; };
+
+inline long long nn_items(int B, int n1, int n2, int qt) {
+    return (long long)B * ((n1 + qt - 1) / qt + (n2 + qt - 1) / qt);
+}
+inline int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+NNShape choose_nn_shape(int B, int n1, int n2, bool exact) {
+    const int kSMs = 148;
+    // (one-direction calls are sized like two-direction ones: the scratch contract has no flags)
+    const int cand = n1 < n2 ? n1 : n2;
+    const int max_split = cand / 512 < 1 ? 1 : cand / 512;
+    int v = nn_items(B, n1, n2, 512) * 10 >= kSMs * 17 ? kDefaultVariant : kSmallVariant;
+    const int forced_v = env_int("URED_NN_VARIANT", -1), forced_s = env_int("URED_NN_NSPLIT", 0);
+    if (!exact && forced_v >= 0 && forced_v < kNumVariants) v = forced_v;   // EXACT is built for shapes 0 and 5 only
+    if (exact && v != kDefaultVariant && v != kSmallVariant) v = kDefaultVariant;
+    const int qt = kVariants[v].R * kVariants[v].T;
+    int ns = 1;
+    while (ns < 8 && cand / (ns * 2) >= 2048) ns *= 2;                                        // 2048-candidate ranges
+    while (ns < 8 && ns * 2 <= max_split && nn_items(B, n1, n2, qt) * ns * 10 < 17 * kSMs) ns *= 2;  // fill the machine
+    if (forced_s > 0) { ns = 1; while (ns < forced_s && ns < 8 && ns * 2 <= max_split) ns *= 2; }
+    NNShape sh = {v, kVariants[v].R, kVariants[v].T, ns};
     return sh;
 }
 
 // ------------------------------------------------------------------------------------------
 // DCD / CD epilogue
 // ------------------------------------------------------------------------------------------
-constexpr int kDcdThreads = 512;
+constexpr int kDcdThreads = 256;  // 8 warps: 6 ordered sums + 2 F-score counts; 8 CTAs/SM so that 640 pairs are ONE wave
 
 // torch's pow(tensor, python scalar) special cases (ATen pow_tensor_scalar): 1 -> x, 2 -> x*x,
 // 0.5 -> sqrt, 0 -> 1; anything else goes through powf
@@ -473,92 +562,135 @@ __device__ __forceinline__ float pow_lambda(float c, float n_lambda) {
 // means run over the valid points only and the DCD fractions are rebuilt from them (non_reg clamps them at 1).
 struct DcdLens { const int *len1, *len2; int rep1, mod2, non_reg; };
 
+// Row sum in the order of torch's reduction kernel, so that the per-pair means carry the SAME BITS as the reference's
+// `dist.mean(1)` / `(1 - e*w).mean(dim=1)` (model_utils.py:39-45,57-58) and rankings built on them cannot differ by a
+// last-bit swap.  ATen reduces a contiguous fp32 row of a [rows >= 16, n] tensor with a 32-lane warp per row
+// (block 32 x 16, 4-wide vector loads): lane t owns the 16-byte vectors t, t+32, ... with one accumulator per vector
+// slot, an unaligned head / a tail of n % 4 elements go to slot 0 of the lanes that own them, the four slots are
+// added left to right, and the lanes are combined by shuffle-down with offsets 1, 2, 4, 8, 16
+// (aten/src/ATen/native/cuda/Reduce.cuh: input_vectorized_thread_reduce_impl, block_x_reduce).  `f(k)` is the k-th
+// element of the row, `mis` the row's misalignment in elements ((address / 4) % 4).  Result valid in lane 0.
+template <typename F>
+__device__ __forceinline__ float torch_row_sum(F f, int n, int mis, int lane) {
+    float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+    int end = n, off = 0;  // element e of the (re-based) row is f(e + off)
+    if (mis > 0) {
+        if (lane >= mis && lane < 4 && lane - mis < n) acc0 = __fadd_rn(acc0, f(lane - mis));
+        off = 4 - mis;
+        end = n + mis - 4;
+    }
+    if (end > 0) {
+        for (int idx = lane; idx * 4 + 3 < end; idx += 32) {
+            const int e = idx * 4 + off;
+            acc0 = __fadd_rn(acc0, f(e)); acc1 = __fadd_rn(acc1, f(e + 1)); acc2 = __fadd_rn(acc2, f(e + 2)); acc3 = __fadd_rn(acc3, f(e + 3));
+        }
+        const int tail = end - end % 4 + lane;
+        if (tail < end) acc0 = __fadd_rn(acc0, f(tail + off));
+    }
+    float v = __fadd_rn(__fadd_rn(__fadd_rn(acc0, acc1), acc2), acc3);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+struct DcdOut {
+    float *loss, *cd_p, *cd_t, *ew1, *ew2;
+    float *fscore;      // optional [3, B]: f-score, precision_1, precision_2 (metrics/CD/fscore.py:3-16)
+    float f_threshold;
+    int B;
+};
+
 __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__restrict__ dist1, const float *__restrict__ dist2,
                                                               const int *__restrict__ idx1, const int *__restrict__ idx2,
                                                               int n1_max, int n2_max, float alpha, float n_lambda, float frac_12,
-                                                              float frac_21, float *__restrict__ loss, float *__restrict__ cd_p,
-                                                              float *__restrict__ cd_t, float *__restrict__ ew1,
-                                                              float *__restrict__ ew2, const DcdLens lens) {
+                                                              float frac_21, const DcdOut out, const DcdLens lens) {
     extern __shared__ int hist[];  // count1[n2] | count2[n1]
-    __shared__ double red[(kDcdThreads / 32) * 6];
+    __shared__ float sums[8];
     int *count1 = hist, *count2 = hist + n2_max;
     const size_t b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *d1 = dist1 + b * n1_max, *d2 = dist2 + b * n2_max;
     const int *i1 = idx1 + b * n1_max, *i2 = idx2 + b * n2_max;
+    const bool ragged = lens.len1 || lens.len2;
     const int n1 = lens.len1 ? max(0, min(lens.len1[b / lens.rep1], n1_max)) : n1_max;
     const int n2 = lens.len2 ? max(0, min(lens.len2[b % lens.mod2], n2_max)) : n2_max;
-    if (lens.len1 || lens.len2) {
+    if (ragged) {
         frac_12 = (float)((double)n2 / (double)max(n1, 1));
         frac_21 = (float)((double)n1 / (double)max(n2, 1));
         if (lens.non_reg) { frac_12 = fmaxf(frac_12, 1.0f); frac_21 = fmaxf(frac_21, 1.0f); }
     }
     if (n1 == 0 || n2 == 0) {  // an empty side: nothing to average (callers mask such pairs out)
-        for (int k = threadIdx.x; k < n1_max; k += kDcdThreads) if (ew1) ew1[b * n1_max + k] = 0.0f;
-        for (int k = threadIdx.x; k < n2_max; k += kDcdThreads) if (ew2) ew2[b * n2_max + k] = 0.0f;
-        if (threadIdx.x == 0) {
-            if (loss) loss[b] = 0.0f;
-            if (cd_p) cd_p[b] = 0.0f;
-            if (cd_t) cd_t[b] = 0.0f;
+        for (int k = tid; k < n1_max; k += kDcdThreads) if (out.ew1) out.ew1[b * n1_max + k] = 0.0f;
+        for (int k = tid; k < n2_max; k += kDcdThreads) if (out.ew2) out.ew2[b * n2_max + k] = 0.0f;
+        if (tid == 0) {
+            if (out.loss) out.loss[b] = 0.0f;
+            if (out.cd_p) out.cd_p[b] = 0.0f;
+            if (out.cd_t) out.cd_t[b] = 0.0f;
+            if (out.fscore) { out.fscore[b] = 0.0f; out.fscore[out.B + b] = 0.0f; out.fscore[2 * (size_t)out.B + b] = 0.0f; }
         }
         return;
     }
-    for (int k = threadIdx.x; k < n1_max + n2_max; k += kDcdThreads) hist[k] = 0;
-    __syncthreads();
-    for (int k = threadIdx.x; k < n1; k += kDcdThreads) atomicAdd(&count1[i1[k]], 1);
-    for (int k = threadIdx.x; k < n2; k += kDcdThreads) atomicAdd(&count2[i2[k]], 1);
-    __syncthreads();
+    const bool want_loss = out.loss || out.ew1 || out.ew2;
+    if (want_loss) {
+        for (int k = tid; k < n1_max + n2_max; k += kDcdThreads) hist[k] = 0;
+        __syncthreads();
+        for (int k = tid; k < n1; k += kDcdThreads) atomicAdd(&count1[i1[k]], 1);
+        for (int k = tid; k < n2; k += kDcdThreads) atomicAdd(&count2[i2[k]], 1);
+        __syncthreads();
+    }
 
-    // per-thread float64 partial sums: [side][term, d, sqrt d]; reduced once (warp shuffles, then a fixed-order
-    // pass over the per-warp partials, so the result is deterministic)
-    double part[6];
-#pragma unroll
-    for (int side = 0; side < 2; side++) {
-        const int n = side ? n2 : n1;
-        const int n_stride = side ? n2_max : n1_max;
-        const float *d = side ? d2 : d1;
-        const int *ix = side ? i2 : i1;
-        const int *cnt = side ? count2 : count1;
-        const float frac = side ? frac_12 : frac_21;
-        float *ew = side ? ew2 : ew1;
-        double a_term = 0.0, a_d = 0.0, a_sqrt = 0.0;
-        if (ew) for (int k = n + threadIdx.x; k < n_stride; k += kDcdThreads) ew[b * n_stride + k] = 0.0f;
-        for (int k = threadIdx.x; k < n; k += kDcdThreads) {
-            const float dk = d[k];
-            const float c = (float)cnt[ix[k]];
-            // model_utils.py:31,35-37: exp(-d*alpha); (count**lambda + 1e-6)**(-1) * frac
-            const float e = expf(__fmul_rn(-dk, alpha));
-            const float w = __fmul_rn(__fdiv_rn(1.0f, __fadd_rn(pow_lambda(c, n_lambda), 1e-6f)), frac);
-            const float ewk = __fmul_rn(e, w);
-            if (ew) ew[b * n_stride + k] = ewk;
-            a_term += (double)__fsub_rn(1.0f, ewk);
-            a_d += (double)dk;
-            a_sqrt += (double)sqrtf(dk);
+    // warps 0-2: side 1 (term, d, sqrt d); warps 3-5: side 2; warps 6, 7: F-score counts of side 1 / 2
+    const int side = warp < 6 ? warp / 3 : warp - 6;
+    const int what = warp < 6 ? warp % 3 : 3;
+    const int n = side ? n2 : n1;
+    const int n_stride = side ? n2_max : n1_max;
+    const float *d = side ? d2 : d1;
+    const int *ix = side ? i2 : i1;
+    const int *cnt = side ? count2 : count1;
+    const float frac = side ? frac_12 : frac_21;
+    float *ew = side ? out.ew2 : out.ew1;
+    const int mis = ragged ? 0 : (int)((reinterpret_cast<uintptr_t>(d) >> 2) & 3u);  // (a ragged pair stands for a per-sample call: aligned)
+    float r = 0.0f;
+    if (what == 0) {
+        if (want_loss) {
+            // model_utils.py:31,35-37: exp(-d*alpha); (count**lambda + 1e-6)**(-1) * frac; the term is 1 - e*w
+            auto term = [&](int k) {
+                const float e = expf(__fmul_rn(-d[k], alpha));
+                const float w = __fmul_rn(__fdiv_rn(1.0f, __fadd_rn(pow_lambda((float)cnt[ix[k]], n_lambda), 1e-6f)), frac);
+                const float ewk = __fmul_rn(e, w);
+                if (ew) ew[b * n_stride + k] = ewk;
+                return __fsub_rn(1.0f, ewk);
+            };
+            r = torch_row_sum(term, n, mis, lane);
+            if (ew) for (int k = n + lane; k < n_stride; k += 32) ew[b * n_stride + k] = 0.0f;
         }
-        part[side * 3 + 0] = a_term; part[side * 3 + 1] = a_d; part[side * 3 + 2] = a_sqrt;
+    } else if (what == 1) {
+        r = torch_row_sum([&](int k) { return d[k]; }, n, mis, lane);
+    } else if (what == 2) {
+        r = torch_row_sum([&](int k) { return sqrtf(d[k]); }, n, mis, lane);
+    } else if (out.fscore) {
+        int c = 0;
+        for (int k = lane; k < n; k += 32) c += d[k] < out.f_threshold ? 1 : 0;
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        r = (float)c;  // a sum of 0/1 floats is exact in any order
     }
-#pragma unroll
-    for (int v = 0; v < 6; v++)
-        for (int o = 16; o > 0; o >>= 1) part[v] += __shfl_xor_sync(0xffffffffu, part[v], o);
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int v = 0; v < 6; v++) red[(threadIdx.x >> 5) * 6 + v] = part[v];
-    }
+    if (lane == 0) sums[warp] = r;
     __syncthreads();
-    double s_term[2], s_d[2], s_sqrt[2];
-    if (threadIdx.x == 0) {
-        double tot[6] = {0, 0, 0, 0, 0, 0};
-        for (int w = 0; w < kDcdThreads / 32; w++)
-            for (int v = 0; v < 6; v++) tot[v] += red[w * 6 + v];
-        s_term[0] = tot[0]; s_d[0] = tot[1]; s_sqrt[0] = tot[2];
-        s_term[1] = tot[3]; s_d[1] = tot[4]; s_sqrt[1] = tot[5];
-    }
-    if (threadIdx.x == 0) {
-        const float loss1 = (float)(s_term[0] / n1), loss2 = (float)(s_term[1] / n2);
-        const float m1 = (float)(s_d[0] / n1), m2 = (float)(s_d[1] / n2);
-        const float r1 = (float)(s_sqrt[0] / n1), r2 = (float)(s_sqrt[1] / n2);
-        if (loss) loss[b] = (loss1 + loss2) / 2.0f;  // model_utils.py:45
-        if (cd_p) cd_p[b] = (r1 + r2) / 2.0f;        // model_utils.py:57
-        if (cd_t) cd_t[b] = m1 + m2;                 // model_utils.py:58
+    if (tid == 0) {
+        // torch's mean: sum * factor with factor = float(outputs) / float(numel) (ReduceMomentKernel.cu mean_kernel_impl);
+        // a ragged pair is the reference's per-sample call (one output row)
+        const float rows = ragged ? 1.0f : (float)out.B;
+        const float f1 = __fdiv_rn(rows, ragged ? (float)n1 : (float)((long long)out.B * n1));
+        const float f2 = __fdiv_rn(rows, ragged ? (float)n2 : (float)((long long)out.B * n2));
+        if (out.loss) out.loss[b] = __fdiv_rn(__fadd_rn(__fmul_rn(sums[0], f1), __fmul_rn(sums[3], f2)), 2.0f);  // model_utils.py:45
+        if (out.cd_p) out.cd_p[b] = __fdiv_rn(__fadd_rn(__fmul_rn(sums[2], f1), __fmul_rn(sums[5], f2)), 2.0f);  // model_utils.py:57
+        if (out.cd_t) out.cd_t[b] = __fadd_rn(__fmul_rn(sums[1], f1), __fmul_rn(sums[4], f2));                   // model_utils.py:58
+        if (out.fscore) {
+            const float p1 = __fmul_rn(sums[6], f1), p2 = __fmul_rn(sums[7], f2);
+            float f = __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, p1), p2), __fadd_rn(p1, p2));  // fscore.py:14
+            if (f != f) f = 0.0f;                                                          // fscore.py:15
+            out.fscore[b] = f; out.fscore[out.B + b] = p1; out.fscore[2 * (size_t)out.B + b] = p2;
+        }
     }
 }
 
@@ -750,6 +882,193 @@ __global__ void __launch_bounds__(kTopkThreads) topk_kernel(const float *__restr
 }
 
 // ------------------------------------------------------------------------------------------
+// fused local top-k + peer exchange + merge (sharded retrieval)
+// ------------------------------------------------------------------------------------------
+// Every rank owns one exchange buffer that all its peers have mapped (CUDA IPC or any other peer mapping the caller
+// provides).  One kernel per query batch replaces "top-k kernel -> NCCL all_gather -> merge kernel":
+//   CTA q selects the k smallest (score, id) keys of row q of the local shard, STORES them straight into slot
+//   [parity][my rank][q] of every peer's buffer over NVLink, publishes a release flag per peer, then spins (acquire)
+//   on the world flags of row q in its OWN buffer, merges the world*k keys it has received and writes the final
+//   [k] (score, id) list -- identical on every rank, because the merge key (score, id) is a total order.
+// Two parity slots make the buffers reusable without any further synchronisation: a peer can run at most one exchange
+// ahead of this rank (it needs this rank's flag of exchange e+1 before it can start e+2), and e+1 uses the other slot.
+// The epoch lives in the buffer header and is advanced by the last CTA, so the launch is replayable from a CUDA graph.
+constexpr int kXchgThreads = 256;
+constexpr int kXchgMaxWorld = 16;
+constexpr int kXchgMaxK = 64;
+constexpr int kXchgMaxRows = 512;   // all CTAs of a launch must be co-resident while they wait for their peers
+constexpr int kXchgHeaderWords = 32;  // [0] epoch, [1] CTAs done, [2] status (0 ok, 1 = a peer never arrived)
+
+struct XchgLayout {
+    int world, rows, k;
+    __host__ __device__ size_t flags_off(int slot, int src, int row) const {
+        return (size_t)kXchgHeaderWords * 4 + (((size_t)slot * world + src) * rows + row) * 4;
+    }
+    __host__ __device__ size_t data_base() const {
+        return ((size_t)kXchgHeaderWords * 4 + (size_t)2 * world * rows * 4 + 255) / 256 * 256;
+    }
+    __host__ __device__ size_t data_off(int slot, int src, int row) const {
+        return data_base() + ((((size_t)slot * world + src) * rows + row) * k) * 8;
+    }
+    __host__ __device__ size_t total() const { return (data_base() + (size_t)2 * world * rows * k * 8 + 255) / 256 * 256; }
+};
+
+struct XchgParams {
+    unsigned char *buf[kXchgMaxWorld];  // buf[r]: rank r's exchange buffer as mapped in THIS process (buf[rank] = own)
+    XchgLayout lay;
+    int rank;
+    const float *scores;
+    int cols, idx_offset;
+    float *out_scores;
+    int *out_ids;
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ float key_score(unsigned long long key) {
+    const unsigned u = (unsigned)(key >> 32);
+    return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ unsigned long long score_key(float s, int i);
+
+__global__ void __launch_bounds__(kXchgThreads) topk_exchange_kernel(const XchgParams p) {
+    __shared__ unsigned long long red[kXchgThreads / 32];
+    __shared__ unsigned long long mine[kXchgMaxK];
+    __shared__ unsigned long long all_keys[kXchgMaxWorld * kXchgMaxK];
+    __shared__ unsigned timed_out;
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const int world = p.lay.world, k = p.lay.k;
+    unsigned char *own = p.buf[p.rank];
+    unsigned *hdr = reinterpret_cast<unsigned *>(own);
+    const unsigned epoch = *reinterpret_cast<volatile unsigned *>(hdr);  // advanced only after every CTA of this launch is done
+    const int slot = (int)(epoch & 1u);
+    if (tid == 0) timed_out = 0u;
+
+    // ---- 1. local top-k of this row: k passes, each the block-wide minimum of the keys above the previous pick ----
+    const float *srow = p.scores + (size_t)row * p.cols;
+    unsigned long long last = 0ull;
+    for (int it = 0; it < k; it++) {
+        unsigned long long m = ~0ull;
+        for (int c = tid; c < p.cols; c += kXchgThreads) {
+            const unsigned long long key = score_key(srow[c], c + p.idx_offset);
+            if ((it == 0 || key > last) && key < m) m = key;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
+            if (other < m) m = other;
+        }
+        if ((tid & 31) == 0) red[tid >> 5] = m;
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 1; i < kXchgThreads / 32; i++) if (red[i] < m) m = red[i];
+            mine[it] = m;  // ~0 when the shard holds fewer than k shapes: padding, sorts last
+        }
+        __syncthreads();
+        last = mine[it];
+        if (last == ~0ull) {  // exhausted: the rest is padding
+            for (int j = it + 1 + tid; j < k; j += kXchgThreads) mine[j] = ~0ull;
+            __syncthreads();
+            break;
+        }
+    }
+
+    // ---- 2. push my k keys into every rank's buffer (own included), then publish one flag per rank ------------------
+    for (int t = tid; t < world * k; t += kXchgThreads) {
+        const int dst = t / k, i = t - dst * k;
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(p.buf[dst] + p.lay.data_off(slot, p.rank, row));
+        d[i] = mine[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world)
+        st_release_sys(reinterpret_cast<unsigned *>(p.buf[tid] + p.lay.flags_off(slot, p.rank, row)), epoch + 1u);
+
+    // ---- 3. wait for the world's keys of this row (bounded: a missing peer sets status instead of hanging the GPU) ----
+    if (tid < world) {
+        const unsigned *f = reinterpret_cast<const unsigned *>(own + p.lay.flags_off(slot, tid, row));
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys(f) != epoch + 1u) {
+            if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > p.timeout_ns) { atomicExch(&timed_out, 1u); break; }
+        }
+    }
+    __syncthreads();
+    if (timed_out) {
+        if (tid == 0) atomicExch(hdr + 2, 1u);
+        for (int i = tid; i < k; i += kXchgThreads) {
+            p.out_scores[(size_t)row * k + i] = __int_as_float(0x7fc00000);
+            p.out_ids[(size_t)row * k + i] = -2;
+        }
+    } else {
+        // ---- 4. merge: rank of every received key among the world*k keys (ids are unique, padding keys are all ~0) ---
+        const int total = world * k;
+        for (int t = tid; t < total; t += kXchgThreads) {
+            const int src = t / k, i = t - src * k;
+            const unsigned long long *d = reinterpret_cast<const unsigned long long *>(own + p.lay.data_off(slot, src, row));
+            all_keys[t] = __ldcg(d + i);  // written by a peer over NVLink: read at L2, never from a stale L1 line
+        }
+        __syncthreads();
+        for (int t = tid; t < total; t += kXchgThreads) {
+            const unsigned long long key = all_keys[t];
+            int rank_of = 0;
+            for (int u = 0; u < total; u++) {
+                const unsigned long long o = all_keys[u];
+                rank_of += (o < key || (o == key && u < t)) ? 1 : 0;
+            }
+            if (rank_of < k) {
+                const bool pad = key == ~0ull;
+                p.out_scores[(size_t)row * k + rank_of] = pad ? kInf : key_score(key);
+                p.out_ids[(size_t)row * k + rank_of] = pad ? -1 : (int)(unsigned)(key & 0xffffffffull);
+            }
+        }
+    }
+
+    // ---- 5. the last CTA of the launch advances the epoch ----------------------------------------------------------
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(hdr + 1, 1u) + 1u;
+        if (done == gridDim.x) {
+            hdr[1] = 0u;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned *>(hdr) = epoch + 1u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FP32 FMA peak probe: the measured denominator of the roofline (MEASURED_PEAKS.json has no FP32 figure)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float *sink, int iters, float a, float b) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = threadIdx.x * 1e-3f + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = __fmaf_rn(v[i], a, b);   // 8 independent chains, 64 FFMA per iteration
+    }
+    float sacc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) sacc += v[i];
+    if (sacc == 123.456f) sink[0] = sacc;  // keeps the chains alive without a store per thread
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side helpers
 // ------------------------------------------------------------------------------------------
 int check_pairs(int B, int n1, int n2, int rep1, int mod2) {
@@ -761,15 +1080,31 @@ int check_pairs(int B, int n1, int n2, int rep1, int mod2) {
 inline int count1_of(int B, int rep1) { return (B + rep1 - 1) / rep1; }
 inline int count2_of(int B, int mod2) { return B < mod2 ? B : mod2; }
 
-template <bool SCREEN, int R>
+template <bool SCREEN, int R, int T, int MINB>
 int launch_nn(const NNParams &p, int B, cudaStream_t st) {
     constexpr int NARR = SCREEN ? 4 : 3;
     const size_t smem = (size_t)kStages * NARR * kTile * sizeof(float);
     const long long grid = (long long)B * (p.qtiles[0] + p.qtiles[1]) * p.nsplit;
     if (grid > 0x7fffffffll) return fail_arg(URED_E_SHAPE, "too many work items for one launch");
-    nn_kernel<SCREEN, R><<<(unsigned)grid, kNNThreads, smem, st>>>(p);
+    nn_kernel<SCREEN, R, T, MINB><<<(unsigned)grid, T, smem, st>>>(p);
     URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "nn_kernel launch");
+}
+
+int launch_nn_variant(int variant, bool exact, const NNParams &p, int B, cudaStream_t st) {
+    // the difference-form (EXACT) kernel carries more live values per query: it is built for the two 4-query shapes only
+    if (exact) return (variant == 5) ? launch_nn<false, 2, 128, 6>(p, B, st) : launch_nn<false, 4, 128, 5>(p, B, st);
+    switch (variant) {
+        case 0: return launch_nn<true, 4, 128, 5>(p, B, st);
+        case 1: return launch_nn<true, 4, 128, 4>(p, B, st);
+        case 2: return launch_nn<true, 8, 128, 3>(p, B, st);
+        case 3: return launch_nn<true, 8, 64, 6>(p, B, st);
+        case 4: return launch_nn<true, 16, 64, 4>(p, B, st);
+        case 5: return launch_nn<true, 2, 128, 6>(p, B, st);
+        case 6: return launch_nn<true, 8, 128, 2>(p, B, st);
+        case 7: return launch_nn<true, 4, 64, 8>(p, B, st);
+    }
+    return fail_arg(URED_E_RANGE, "unknown nn_kernel variant");
 }
 
 }  // namespace
@@ -803,8 +1138,19 @@ int ured_pack_clouds(const float *xyz, int count, int n, const int *len, void *p
 
 size_t ured_nn_scratch_bytes(int B, int n1, int n2) {
     if (B <= 0 || n1 <= 0 || n2 <= 0) return 0;
-    const NNShape sh = choose_nn_shape(B, n1, n2);
-    return sh.nsplit > 1 ? align_up((size_t)sh.nsplit * B * ((size_t)n1 + n2) * 8, 256) : 0;
+    const int a = choose_nn_shape(B, n1, n2, false).nsplit, b = choose_nn_shape(B, n1, n2, true).nsplit;
+    const int nsplit = a > b ? a : b;  // the caller need not know which kernel flavour will run
+    return nsplit > 1 ? align_up((size_t)nsplit * B * ((size_t)n1 + n2) * 8, 256) : 0;
+}
+
+int ured_nn_launch_shape(int B, int n1, int n2, unsigned flags, int *variant, int *queries_per_cta, int *threads, int *nsplit) {
+    if (B <= 0 || n1 <= 0 || n2 <= 0) return fail_arg(URED_E_SHAPE, "ured_nn_launch_shape: empty problem");
+    const NNShape sh = choose_nn_shape(B, n1, n2, (flags & URED_FLAG_EXACT_ONLY) != 0);
+    if (variant) *variant = sh.variant;
+    if (queries_per_cta) *queries_per_cta = sh.R * sh.T;
+    if (threads) *threads = sh.T;
+    if (nsplit) *nsplit = sh.nsplit;
+    return 0;
 }
 
 int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *xyz2, const void *packed2, int n2, int B,
@@ -834,11 +1180,11 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
     p.rep1 = rep1; p.mod2 = mod2;
     p.len[0] = len1; p.len[1] = len2;
     const bool exact = (flags & URED_FLAG_EXACT_ONLY) != 0;
-    const NNShape sh = choose_nn_shape(B, n1, n2);
-    const int R = sh.R;
+    const NNShape sh = choose_nn_shape(B, n1, n2, exact);
+    const int QT = sh.R * sh.T;
     const bool one_dir = (flags & URED_FLAG_ONE_DIRECTION) != 0;  // only cloud-1 points search cloud 2 (K=1 kNN)
-    p.qtiles[0] = (n1 + R * kNNThreads - 1) / (R * kNNThreads);
-    p.qtiles[1] = one_dir ? 0 : (n2 + R * kNNThreads - 1) / (R * kNNThreads);
+    p.qtiles[0] = (n1 + QT - 1) / QT;
+    p.qtiles[1] = one_dir ? 0 : (n2 + QT - 1) / QT;
     p.nsplit = sh.nsplit;
     p.B = B;
     const size_t tot1 = (size_t)B * n1, tot2 = (size_t)B * n2;
@@ -855,8 +1201,7 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
         p.part_dist[0] = p.part_dist[1] = nullptr;
         p.part_idx[0] = p.part_idx[1] = nullptr;
     }
-    if (exact) rc = R == 4 ? launch_nn<false, 4>(p, B, st) : launch_nn<false, 2>(p, B, st);
-    else rc = R == 4 ? launch_nn<true, 4>(p, B, st) : launch_nn<true, 2>(p, B, st);
+    rc = launch_nn_variant(sh.variant, exact, p, B, st);
     if (rc || sh.nsplit == 1) return rc;
     merge_splits_kernel<<<(unsigned)((tot1 + 255) / 256), 256, 0, st>>>(p.part_dist[0], p.part_idx[0], tot1, sh.nsplit, dist1, idx1);
     URED_COUNT_LAUNCH();
@@ -900,27 +1245,37 @@ int ured_chamfer_forward(const float *xyz1, const float *xyz2, int B, int n1, in
                           ured_nn_scratch_bytes(B, n1, n2), flags, stream);
 }
 
-int ured_dcd_forward(const float *dist1, const float *dist2, const int *idx1, const int *idx2, int B, int n1, int n2,
-                     int rep1, int mod2, const int *len1, const int *len2, float alpha, float n_lambda, float frac_12,
-                     float frac_21, unsigned flags, float *loss, float *cd_p, float *cd_t, float *ew1, float *ew2, void *stream) {
+int ured_dcd_forward_ex(const float *dist1, const float *dist2, const int *idx1, const int *idx2, int B, int n1, int n2,
+                        int rep1, int mod2, const int *len1, const int *len2, float alpha, float n_lambda, float frac_12,
+                        float frac_21, unsigned flags, float *loss, float *cd_p, float *cd_t, float *ew1, float *ew2,
+                        float *fscore, float f_threshold, void *stream) {
     if (B < 0 || n1 < 0 || n2 < 0) return fail_arg(URED_E_SHAPE, "negative size");
     if (rep1 < 1 || mod2 < 1) return fail_arg(URED_E_SHAPE, "rep1 and mod2 must be >= 1");
     if (B == 0) return 0;
     if (n1 == 0 || n2 == 0) return fail_arg(URED_E_SHAPE, "ured_dcd_forward: empty cloud");
     if (!dist1 || !dist2 || !idx1 || !idx2) return fail_arg(URED_E_NULL, "ured_dcd_forward: NULL input");
-    const size_t smem = (size_t)(n1 + n2) * sizeof(int);
+    const bool want_loss = loss || ew1 || ew2;
+    const size_t smem = want_loss ? (size_t)(n1 + n2) * sizeof(int) : 0;  // cd_p / cd_t / fscore alone need no histogram
     if (smem > 200 * 1024) return fail_arg(URED_E_RANGE, "ured_dcd_forward: n1 + n2 > 51200 points per pair not supported");
-    static thread_local bool attr_done = false;
-    if (!attr_done) {
+    // (per device, not per thread or process: set before every launch that needs it -- the call is cheap and legal during capture)
+    if (smem > 48 * 1024)
         URED_CUDA(cudaFuncSetAttribute(dcd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "dcd smem attribute");
-        attr_done = true;
-    }
     DcdLens lens;
     lens.len1 = len1; lens.len2 = len2; lens.rep1 = rep1; lens.mod2 = mod2; lens.non_reg = (flags & URED_FLAG_NON_REG) ? 1 : 0;
+    DcdOut out;
+    out.loss = loss; out.cd_p = cd_p; out.cd_t = cd_t; out.ew1 = ew1; out.ew2 = ew2;
+    out.fscore = fscore; out.f_threshold = f_threshold; out.B = B;
     dcd_fwd_kernel<<<B, kDcdThreads, smem, (cudaStream_t)stream>>>(dist1, dist2, idx1, idx2, n1, n2, alpha, n_lambda, frac_12,
-                                                                   frac_21, loss, cd_p, cd_t, ew1, ew2, lens);
+                                                                   frac_21, out, lens);
     URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "dcd_fwd_kernel launch");
+}
+
+int ured_dcd_forward(const float *dist1, const float *dist2, const int *idx1, const int *idx2, int B, int n1, int n2,
+                     int rep1, int mod2, const int *len1, const int *len2, float alpha, float n_lambda, float frac_12,
+                     float frac_21, unsigned flags, float *loss, float *cd_p, float *cd_t, float *ew1, float *ew2, void *stream) {
+    return ured_dcd_forward_ex(dist1, dist2, idx1, idx2, B, n1, n2, rep1, mod2, len1, len2, alpha, n_lambda, frac_12, frac_21, flags,
+                               loss, cd_p, cd_t, ew1, ew2, nullptr, 0.0f, stream);
 }
 
 int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n2, int rep1, int mod2, const int *len1,
@@ -956,11 +1311,8 @@ int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n
     p.len[0] = len1; p.len[1] = len2;
     const size_t smem_need = (size_t)(n1 + n2) * 3 * sizeof(float);
     if (!shared1 && !shared2 && smem_need <= 96 * 1024) {
-        static thread_local bool attr_done = false;
-        if (!attr_done) {
+        if (smem_need > 48 * 1024)
             URED_CUDA(cudaFuncSetAttribute(grad_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "grad smem attribute");
-            attr_done = true;
-        }
         grad_smem_kernel<<<B, kGradSmemThreads, smem_need, st>>>(p);
         URED_COUNT_LAUNCH();
         return check_cuda(cudaGetLastError(), "grad_smem_kernel launch");
@@ -1006,6 +1358,82 @@ int ured_merge_topk(const float *scores, const int *ids, int rows, int cols, int
     topk_kernel<<<rows, kTopkThreads, 0, (cudaStream_t)stream>>>(scores, ids, cols, k, 0, out_scores, out_ids);
     URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "topk_kernel(merge) launch");
+}
+
+int ured_probe_ffma(float *sink, int blocks, int iters, double *flop, void *stream) {
+    if (!sink || blocks < 1 || iters < 1) return fail_arg(URED_E_SHAPE, "ured_probe_ffma: bad argument");
+    ffma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, iters, 0.999f, 1e-3f);
+    URED_COUNT_LAUNCH();
+    if (flop) *flop = (double)blocks * 256.0 * (double)iters * 64.0 * 2.0;
+    return check_cuda(cudaGetLastError(), "ffma_probe_kernel launch");
+}
+
+// ---- peer exchange (sharded retrieval) -----------------------------------------------------------------------------
+size_t ured_xchg_bytes(int world, int rows, int k) {
+    if (world < 1 || world > kXchgMaxWorld || rows < 1 || rows > kXchgMaxRows || k < 1 || k > kXchgMaxK) return 0;
+    XchgLayout lay;
+    lay.world = world; lay.rows = rows; lay.k = k;
+    return lay.total();
+}
+
+int ured_xchg_alloc(size_t bytes, void **dev_ptr) {
+    if (!dev_ptr || bytes == 0) return fail_arg(URED_E_NULL, "ured_xchg_alloc: NULL pointer or zero size");
+    // An IPC-exportable allocation has to be a whole cudaMalloc block (not a slice of a caching allocator's pool):
+    // this buffer is the one piece of device memory the library allocates itself.
+    URED_CUDA(cudaMalloc(dev_ptr, bytes), "cudaMalloc(exchange buffer)");
+    URED_CUDA(cudaMemset(*dev_ptr, 0, bytes), "cudaMemset(exchange buffer)");
+    return check_cuda(cudaDeviceSynchronize(), "exchange buffer init");
+}
+int ured_xchg_free(void *dev_ptr) { return dev_ptr ? check_cuda(cudaFree(dev_ptr), "cudaFree(exchange buffer)") : 0; }
+
+int ured_xchg_export(void *dev_ptr, void *handle64) {
+    if (!dev_ptr || !handle64) return fail_arg(URED_E_NULL, "ured_xchg_export: NULL pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == URED_XCHG_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    URED_CUDA(cudaIpcGetMemHandle(&h, dev_ptr), "cudaIpcGetMemHandle");
+    memcpy(handle64, &h, sizeof(h));
+    return 0;
+}
+int ured_xchg_import(const void *handle64, void **peer_ptr) {
+    if (!handle64 || !peer_ptr) return fail_arg(URED_E_NULL, "ured_xchg_import: NULL pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    return check_cuda(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+int ured_xchg_close(void *peer_ptr) { return peer_ptr ? check_cuda(cudaIpcCloseMemHandle(peer_ptr), "cudaIpcCloseMemHandle") : 0; }
+
+int ured_xchg_status(const void *own_buf, int *status, unsigned *epoch, void *stream) {
+    if (!own_buf || !status) return fail_arg(URED_E_NULL, "ured_xchg_status: NULL pointer");
+    unsigned hdr[3];
+    URED_CUDA(cudaMemcpyAsync(hdr, own_buf, sizeof(hdr), cudaMemcpyDeviceToHost, (cudaStream_t)stream), "exchange status copy");
+    URED_CUDA(cudaStreamSynchronize((cudaStream_t)stream), "exchange status sync");
+    *status = (int)hdr[2];
+    if (epoch) *epoch = hdr[0];
+    return 0;
+}
+
+int ured_topk_exchange(const float *scores, int rows, int cols, int k, int idx_offset, void *const *bufs, int world, int rank,
+                       int buf_rows, float *out_scores, int *out_ids, unsigned timeout_ms, void *stream) {
+    if (rows < 0 || cols < 0 || k < 1) return fail_arg(URED_E_SHAPE, "ured_topk_exchange: bad size");
+    if (world < 1 || world > kXchgMaxWorld || rank < 0 || rank >= world) return fail_arg(URED_E_RANGE, "ured_topk_exchange: world <= 16, 0 <= rank < world");
+    if (k > kXchgMaxK) return fail_arg(URED_E_RANGE, "ured_topk_exchange: k <= 64");
+    if (rows != buf_rows || rows > kXchgMaxRows) return fail_arg(URED_E_RANGE, "ured_topk_exchange: rows must equal the buffer's row count (<= 512)");
+    if (rows == 0) return 0;
+    if (!bufs || !out_scores || !out_ids || (cols > 0 && !scores)) return fail_arg(URED_E_NULL, "ured_topk_exchange: NULL pointer");
+    XchgParams p;
+    memset(&p, 0, sizeof(p));
+    for (int r = 0; r < world; r++) {
+        if (!bufs[r]) return fail_arg(URED_E_NULL, "ured_topk_exchange: NULL peer buffer");
+        p.buf[r] = (unsigned char *)bufs[r];
+    }
+    p.lay.world = world; p.lay.rows = buf_rows; p.lay.k = k;
+    p.rank = rank;
+    p.scores = scores; p.cols = cols; p.idx_offset = idx_offset;
+    p.out_scores = out_scores; p.out_ids = out_ids;
+    p.timeout_ns = (unsigned long long)(timeout_ms ? timeout_ms : 5000u) * 1000000ull;
+    topk_exchange_kernel<<<rows, kXchgThreads, 0, (cudaStream_t)stream>>>(p);
+    URED_COUNT_LAUNCH();
+    return check_cuda(cudaGetLastError(), "topk_exchange_kernel launch");
 }
 
 }  // extern "C"

@@ -26,6 +26,42 @@ def fscore(dist1, dist2, threshold=0.0001):
     return f, precision_1, precision_2
 
 
+def torch_epilogue(dist1, dist2, idx1, idx2, alpha, n_lambda, frac_12, frac_21):
+    """(loss, cd_p, cd_t) [B] through torch's own kernels, op for op as the reference's calc_dcd / calc_cd bodies
+    (model_utils.py:26-45, 57-58), applied to given NN results of chamfer(gt, x).
+
+    This is the audit / ``exact_ranking`` path: whatever torch's reduction kernels do for this shape and batch size,
+    this does too, because it calls them (exp, scatter_add_, gather, pow, mean -- about 25 launches).  No gradient.
+    """
+    def density_term(dist, idx, bins_like, frac):
+        hits = torch.zeros_like(bins_like).scatter_add_(1, idx.long(), torch.ones_like(idx))   # int32 histogram of the argmins
+        weight = hits.gather(1, idx.long()).float() ** n_lambda
+        weight = (weight + 1e-6) ** (-1) * frac
+        return (1 - torch.exp(-dist * alpha) * weight).mean(dim=1)
+
+    with torch.no_grad():
+        loss = (density_term(dist1, idx1, idx2, frac_21) + density_term(dist2, idx2, idx1, frac_12)) / 2
+        cd_p = (torch.sqrt(dist1).mean(1) + torch.sqrt(dist2).mean(1)) / 2
+        cd_t = dist1.mean(1) + dist2.mean(1)
+    return loss, cd_p, cd_t
+
+
+def fscore_fused(dist1, dist2, threshold=0.0001):
+    """`fscore` as part of the epilogue kernel (one launch): (fscore, precision_1, precision_2), each [B]."""
+    lib = _native.load()
+    B, n1 = dist1.shape
+    n2 = dist2.shape[1]
+    dev = dist1.device
+    out = torch.empty(3, B, device=dev, dtype=torch.float32)
+    dummy = torch.empty(1, device=dev, dtype=torch.int32)   # idx is not read when no DCD term is requested
+    with torch.cuda.device(dev):
+        rc = lib.ured_dcd_forward_ex(_native.ptr(dist1.contiguous()), _native.ptr(dist2.contiguous()), _native.ptr(dummy), _native.ptr(dummy),
+                                     B, n1, n2, 1, max(B, 1), None, None, 0.0, 1.0, 1.0, 1.0, 0,
+                                     None, None, None, None, None, _native.ptr(out), float(threshold), _stream(dev))
+    _native.check(rc, "ured_dcd_forward_ex")
+    return out[0], out[1], out[2]
+
+
 class _ChamferDCD(Function):
     """chamfer(gt, x) + the calc_cd/calc_dcd epilogue as one autograd node.
 
@@ -139,7 +175,7 @@ def calc_cd(output, gt, calc_f1=False, return_raw=False, normalize=False, separa
         _loss, cd_p, cd_t, dist1, dist2, idx1, idx2 = _fused(output, gt, 0.0, 1.0, 1.0, 1.0)
         res = [cd_p, cd_t]
     if calc_f1:
-        f1, _, _ = fscore(dist1, dist2)
+        f1, _, _ = fscore_fused(dist1.detach(), dist2.detach())   # fscore.py:3-16 inside the epilogue kernel
         res.append(f1)
     if return_raw:
         res.extend([dist1, dist2, idx1, idx2])

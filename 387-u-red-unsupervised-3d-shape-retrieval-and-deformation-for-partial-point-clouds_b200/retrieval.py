@@ -90,8 +90,18 @@ def nn_pairs(cloud1, cloud2, B, rep1, mod2, exact_only=False):
     return dist1, dist2, idx1, idx2
 
 
-def pair_scores(dist1, dist2, idx1, idx2, alpha=1000, n_lambda=1):
-    """(dcd, cd_p, cd_t), each [B], from raw NN results of chamfer(gt, x) (model_utils.py:31-58)."""
+def pair_scores(dist1, dist2, idx1, idx2, alpha=1000, n_lambda=1, exact_ranking=False):
+    """(dcd, cd_p, cd_t), each [B], from raw NN results of chamfer(gt, x) (model_utils.py:31-58).
+
+    Default: the fused epilogue kernel, whose row means follow torch's reduction order (include/ured_chamfer.h,
+    "Reduction order") -- bit-identical to the reference's torch ops for the cloud sizes U-RED uses.
+    ``exact_ranking=True`` runs the reference's torch ops themselves on the bit-exact dist/idx (model_utils.py:26-45,
+    57-58: exp, scatter_add_, gather, pow, mean): ~25 small launches per call, for audits and for shapes outside the
+    fused kernel's guaranteed range."""
+    if exact_ranking:
+        from .model_utils import torch_epilogue
+        n1, n2 = dist1.shape[1], dist2.shape[1]
+        return torch_epilogue(dist1, dist2, idx1, idx2, alpha, n_lambda, frac_12=n2 / n1, frac_21=n1 / n2)
     lib = _native.load()
     B, n1 = dist1.shape
     n2 = dist2.shape[1]
@@ -107,7 +117,7 @@ def pair_scores(dist1, dist2, idx1, idx2, alpha=1000, n_lambda=1):
     return out[0], out[1], out[2]
 
 
-def score_candidates(targets, candidates, alpha=1000, n_lambda=1, exact_only=False):
+def score_candidates(targets, candidates, alpha=1000, n_lambda=1, exact_only=False, exact_ranking=False):
     """Score Q targets [Q, N, 3] against their K candidates [Q, K, M, 3].
 
     Returns {"dcd", "cd_p", "cd_t"}: each [Q, K], equal to calc_dcd(candidates[q, k], targets[q]).
@@ -120,11 +130,11 @@ def score_candidates(targets, candidates, alpha=1000, n_lambda=1, exact_only=Fal
     cands = PackedClouds(candidates.reshape(Q * K, M, 3).float())
     tgts = _as_packed(targets.float() if not isinstance(targets, PackedClouds) else targets)
     raw = nn_pairs(tgts, cands, Q * K, K, Q * K, exact_only=exact_only)
-    dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda)
+    dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda, exact_ranking=exact_ranking)
     return {"dcd": dcd.view(Q, K), "cd_p": cd_p.view(Q, K), "cd_t": cd_t.view(Q, K)}
 
 
-def score_library(targets, library, alpha=1000, n_lambda=1, max_pairs=8192, exact_only=False):
+def score_library(targets, library, alpha=1000, n_lambda=1, max_pairs=8192, exact_only=False, exact_ranking=False):
     """Score every target [Q, N, 3] against every library shape: {"dcd","cd_p","cd_t"} each [Q, S].
 
     ``library`` is a PackedClouds (packed once, kept resident) or a [S, M, 3] tensor.  Work is cut
@@ -143,7 +153,7 @@ def score_library(targets, library, alpha=1000, n_lambda=1, max_pairs=8192, exac
         sub_t = tgts.slice(q0, q1)
         if S <= max_pairs:
             raw = nn_pairs(sub_t, lib_c, (q1 - q0) * S, S, S, exact_only=exact_only)
-            dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda)
+            dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda, exact_ranking=exact_ranking)
             out[0, q0:q1] = dcd.view(q1 - q0, S)
             out[1, q0:q1] = cd_p.view(q1 - q0, S)
             out[2, q0:q1] = cd_t.view(q1 - q0, S)
@@ -152,7 +162,7 @@ def score_library(targets, library, alpha=1000, n_lambda=1, max_pairs=8192, exac
                 s1 = min(S, s0 + max_pairs)
                 slab = lib_c.slice(s0, s1)
                 raw = nn_pairs(sub_t, slab, s1 - s0, s1 - s0, s1 - s0, exact_only=exact_only)
-                dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda)
+                dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda, exact_ranking=exact_ranking)
                 out[0, q0, s0:s1] = dcd
                 out[1, q0, s0:s1] = cd_p
                 out[2, q0, s0:s1] = cd_t
@@ -236,34 +246,30 @@ def shard_bounds(num_shapes, world_size, rank):
 
 
 def merge_topk(scores, ids, k):
-    """Merge candidate lists [Q, C] by ascending (score, id); ids < 0 mark padding.
+    """Merge candidate lists [Q, C] by ascending (score, id); ids < 0 mark padding (native kernel, GPU tensors only)."""
+    if not scores.is_cuda:
+        raise RuntimeError("merge_topk: GPU tensors only")
+    lib = _native.load()
+    scores = scores.contiguous().float()
+    ids = ids.contiguous().to(torch.int32)
+    Q, C = scores.shape
+    out_s = torch.empty(Q, k, device=scores.device, dtype=torch.float32)
+    out_i = torch.empty(Q, k, device=scores.device, dtype=torch.int32)
+    with torch.cuda.device(scores.device):
+        rc = lib.ured_merge_topk(_native.ptr(scores), _native.ptr(ids), Q, C, k, _native.ptr(out_s), _native.ptr(out_i),
+                                 _stream(scores.device))
+    _native.check(rc, "ured_merge_topk")
+    return out_s, out_i
 
-    CUDA tensors go through the native kernel (ured_merge_topk); CPU tensors (the gloo-backed tests of the
-    exchange logic) use the equivalent two stable sorts below.
+
+def gather_and_merge(local_scores, local_ids, k, group=None, merge=None):
+    """all_gather every rank's local top-k [Q, k_local<=k] (padded to k) and merge; same result on all ranks.
+
+    This is the NCCL form of the exchange (three launches and one collective); `PeerExchange.topk` is the fused one.
+    `merge` (default: the native merge_topk) exists so that the gloo-backed CPU tests can check the gather/padding
+    logic with their own reference merge.
     """
-    if scores.is_cuda:
-        lib = _native.load()
-        scores = scores.contiguous().float()
-        ids = ids.contiguous().to(torch.int32)
-        Q, C = scores.shape
-        out_s = torch.empty(Q, k, device=scores.device, dtype=torch.float32)
-        out_i = torch.empty(Q, k, device=scores.device, dtype=torch.int32)
-        with torch.cuda.device(scores.device):
-            rc = lib.ured_merge_topk(_native.ptr(scores), _native.ptr(ids), Q, C, k, _native.ptr(out_s), _native.ptr(out_i),
-                                     _stream(scores.device))
-        _native.check(rc, "ured_merge_topk")
-        return out_s, out_i
-    scores = torch.where(ids < 0, torch.full_like(scores, float("inf")), scores)
-    big = torch.iinfo(ids.dtype).max
-    order = torch.sort(torch.where(ids < 0, torch.full_like(ids, big), ids), dim=1, stable=True).indices
-    s = torch.gather(scores, 1, order)
-    i = torch.gather(ids, 1, order)
-    order = torch.sort(s, dim=1, stable=True).indices
-    return torch.gather(s, 1, order)[:, :k], torch.gather(i, 1, order)[:, :k]
-
-
-def gather_and_merge(local_scores, local_ids, k, group=None):
-    """all_gather every rank's local top-k [Q, k_local<=k] (padded to k) and merge; same result on all ranks."""
+    merge = merge or merge_topk
     Q = local_scores.shape[0]
     pad = k - local_scores.shape[1]
     if pad > 0:
@@ -279,7 +285,7 @@ def gather_and_merge(local_scores, local_ids, k, group=None):
     else:
         out = msg.unsqueeze(0)
     allmsg = out.permute(1, 0, 2, 3).reshape(Q, -1, 2)
-    return merge_topk(allmsg[..., 0].contiguous().view(torch.float32), allmsg[..., 1].contiguous(), k)
+    return merge(allmsg[..., 0].contiguous().view(torch.float32), allmsg[..., 1].contiguous(), k)
 
 
 def retrieve_sharded(targets, local_library, shard_offset, k=10, metric="cd_t", group=None, **score_kw):
@@ -300,19 +306,20 @@ class RetrievalEngine:
     """Resident library shard + a CUDA graph of the whole per-query-batch pipeline.
 
     Retrieval against a sharded library is latency-bound when the shard is small (1000 shapes over 8 GPUs is
-    ~0.15 ms of kernel time per query): eager execution pays ~10 kernel launches, a dozen allocations and the Python
-    glue per step.  The engine keeps every buffer static and captures
-        copy targets -> pack -> nn_kernel (+ split merge) -> dcd_fwd_kernel -> top-k [-> all_gather -> merge]
-    once; ``query()`` copies the targets into the static input and replays the graph.  With more than one rank the
-    NCCL all_gather and the merge are captured in the same graph (the only multi-rank graph mode: mixing graph
-    replays with eager NCCL calls is not supported here).  Measured on 8 B200 (profiles/): for a 1000-shape library
-    and ONE query per step the exchange dominates either way (eager 0.32 ms, graph 0.39 ms per query); batch queries
-    (Q >= 8) to amortise it.
+    ~0.15 ms of kernel time per query).  The engine keeps every buffer static and captures
+        copy targets -> pack -> nn_kernel (+ split merge) -> dcd_fwd_kernel -> top-k / exchange
+    once; ``query()`` copies the targets into the static input and replays the graph.
+
+    exchange (only with more than one rank):
+      "peer"  (default) one fused kernel: local top-k, NVLink stores of the [Q, k] keys into every peer's exchange buffer,
+              flag wait, merge (`PeerExchange`, include/ured_chamfer.h "sharded retrieval") -- captured in the graph;
+      "nccl"  top-k kernel, `all_gather_into_tensor`, merge kernel (the plain collective; also captured).
+    Every rank ends with the same (scores [Q, k], global shape ids int32 [Q, k]).  Results are fresh tensors (the graph's
+    static outputs are cloned), so a caller may hold them across queries.
     """
 
     def __init__(self, local_library, shard_offset, num_queries, k=10, metric="cd_t", alpha=1000, n_lambda=1,
-                 group=None, use_graph=True, max_pairs=16384):
-        graph_collective = True
+                 group=None, use_graph=True, max_pairs=16384, exchange="peer", exact_ranking=False):
         if local_library is None:
             self.lib = None
         elif isinstance(local_library, PackedClouds):
@@ -321,51 +328,62 @@ class RetrievalEngine:
             self.lib = PackedClouds(local_library) if len(local_library) else None  # an empty shard holds nothing
         self.offset, self.Q, self.k, self.metric = int(shard_offset), int(num_queries), int(k), metric
         self.alpha, self.n_lambda, self.group, self.max_pairs = alpha, n_lambda, group, max_pairs
+        self.exact_ranking = bool(exact_ranking)
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        self.exchange = exchange if self.world > 1 else "none"
+        self.xchg = None
         self.graph = None
         self.static_in = None
         self.kernels_per_replay = 0
-        self.use_graph, self.graph_collective = use_graph, graph_collective and self.world > 1
+        self.use_graph = use_graph
 
-    def _local(self, targets):
-        Q, k = self.Q, self.k
-        dev = targets.device
+    def _peer(self, device):
+        if self.xchg is None:
+            from .exchange import PeerExchange
+            self.xchg = PeerExchange(self.Q, self.k, device, group=self.group)
+        return self.xchg
+
+    def _scores(self, targets):
         if self.lib is None or self.lib.count == 0:
-            ls = torch.full((Q, k), float("inf"), device=dev)
-            li = torch.full((Q, k), -1, device=dev, dtype=torch.int32)
-            return ls, li
-        scores = score_library(targets, self.lib, alpha=self.alpha, n_lambda=self.n_lambda, max_pairs=self.max_pairs)[self.metric]
-        kk = min(k, self.lib.count)
-        ls, li = topk_smallest(scores, kk, idx_offset=self.offset)
-        if kk < k:
-            ls = torch.cat([ls, ls.new_full((Q, k - kk), float("inf"))], 1)
-            li = torch.cat([li, li.new_full((Q, k - kk), -1)], 1)
-        return ls, li
-
-    def _exchange(self, ls, li):
-        if self.world == 1:
-            return ls, li
-        msg = torch.stack([ls.contiguous().view(torch.int32), li], dim=-1).contiguous()
-        out = torch.empty((self.world * self.Q, self.k, 2), dtype=torch.int32, device=msg.device)
-        dist.all_gather_into_tensor(out, msg, group=self.group)
-        allmsg = out.view(self.world, self.Q, self.k, 2).permute(1, 0, 2, 3).reshape(self.Q, -1, 2)
-        return merge_topk(allmsg[..., 0].contiguous().view(torch.float32), allmsg[..., 1].contiguous(), self.k)
+            return torch.empty(self.Q, 0, device=targets.device, dtype=torch.float32)
+        return score_library(targets, self.lib, alpha=self.alpha, n_lambda=self.n_lambda, max_pairs=self.max_pairs,
+                             exact_ranking=self.exact_ranking)[self.metric]
 
     def _pipeline(self, targets):
-        ls, li = self._local(targets)
-        if self.graph_collective or self.world == 1:
-            return self._exchange(ls, li)
-        return ls, li
+        Q, k = self.Q, self.k
+        scores = self._scores(targets)
+        if self.exchange == "peer":
+            return self._peer(targets.device).topk(scores, self.offset)
+        S_local = scores.shape[1]
+        if S_local == 0:
+            ls = torch.full((Q, k), float("inf"), device=targets.device)
+            li = torch.full((Q, k), -1, device=targets.device, dtype=torch.int32)
+        else:
+            kk = min(k, S_local)
+            ls, li = topk_smallest(scores, kk, idx_offset=self.offset)
+            if kk < k:
+                ls = torch.cat([ls, ls.new_full((Q, k - kk), float("inf"))], 1)
+                li = torch.cat([li, li.new_full((Q, k - kk), -1)], 1)
+        if self.exchange == "none":
+            return ls, li
+        msg = torch.stack([ls.contiguous().view(torch.int32), li], dim=-1).contiguous()
+        out = torch.empty((self.world * Q, k, 2), dtype=torch.int32, device=msg.device)
+        dist.all_gather_into_tensor(out, msg, group=self.group)
+        allmsg = out.view(self.world, Q, k, 2).permute(1, 0, 2, 3).reshape(Q, -1, 2)
+        return merge_topk(allmsg[..., 0].contiguous().view(torch.float32), allmsg[..., 1].contiguous(), k)
 
     def query(self, targets):
         """targets [Q, N, 3] float32 CUDA -> (scores [Q, k], global shape ids int32 [Q, k]), identical on all ranks."""
         if targets.shape[0] != self.Q:
             raise ValueError(f"engine was built for {self.Q} queries per call")
         if not self.use_graph:
-            ls, li = self._local(targets.float())
-            return self._exchange(ls, li)
+            return self._pipeline(targets.float())
         if self.graph is None:
             self.static_in = targets.float().contiguous().clone()
+            if self.exchange == "peer":
+                self._peer(targets.device)          # buffer mapping (collective set-up) happens outside the capture
             side = torch.cuda.Stream(device=targets.device)
             side.wait_stream(torch.cuda.current_stream(targets.device))
             with torch.cuda.stream(side):       # warm-up outside capture: attribute calls, NCCL connections, allocator pools
@@ -380,7 +398,14 @@ class RetrievalEngine:
             self.kernels_per_replay = int(_native.load().ured_kernel_launches() - n0)  # library kernels inside the graph
         self.static_in.copy_(targets, non_blocking=True)
         self.graph.replay()
-        out = self.static_out
-        if not self.graph_collective and self.world > 1:
-            out = self._exchange(*out)
-        return out
+        return tuple(t.clone() for t in self.static_out)
+
+    def check(self):
+        """Synchronise; raise if a peer exchange timed out (ids would be -2)."""
+        if self.xchg is not None:
+            self.xchg.check()
+
+    def close(self):
+        if self.xchg is not None:
+            self.xchg.close()
+            self.xchg = None

@@ -170,108 +170,369 @@ def run_reference_arm(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------
-# sharded library retrieval (cfg3 / cfg5): forward scoring + local top-k + one all_gather + merge
+# shared helpers of the GPU arm
 # ------------------------------------------------------------------------------------------------
-def run_retrieval(args):
-    import torch
-    import torch.distributed as dist
-    import ured_b200 as ured
+class Ctx:
+    """Process-wide state of one bench run (device, ranks, library handle)."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-    lib = ured._native.load()
-    S, Q, n, desc = RETRIEVAL[args.workload]
-    S = args.library_size or S
-    Q = args.queries or Q
-    k = 10
-    lo, hi = ured.shard_bounds(S, world, rank)
-    # the library is defined in global slabs of 512 shapes (seed = slab id), so every world size sees the SAME
-    # library; a rank generates the slabs overlapping its shard, packs the shard once and keeps it resident
-    SLAB = 512
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        import ured_b200 as ured
+        self.torch, self.dist, self.ured = torch, dist, ured
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = ured._native.load()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps, warmup, sampler=None, whole_loop=False, flush=True, collective=True):
+        """W untimed warm-up steps, then EXACTLY `steps` timed ones, bracketed by barrier + synchronize, CUDA events on
+        the launching stream, max over ranks.  flush: rewrite a 256 MiB buffer between timed iterations (outside the
+        event pairs); whole_loop: one event pair around all steps (pipelined e2e loops).  collective=False: this rank
+        alone is measuring (no barrier, no max)."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(1 if whole_loop else steps)]
+        self.barrier() if collective else torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        launches0 = self.lib.ured_kernel_launches()
+        if whole_loop:
+            ev[0][0].record()
+            for _ in range(steps):
+                fn()
+            ev[0][1].record()
+        else:
+            for s in range(steps):
+                if flush:
+                    self.flush.zero_()
+                ev[s][0].record()
+                fn()
+                ev[s][1].record()
+        self.barrier() if collective else torch.cuda.synchronize()
+        launches = self.lib.ured_kernel_launches() - launches0
+        if sampler:
+            sampler.stop()
+        total_ms = sum(a.elapsed_time(b) for a, b in ev)
+        ms = total_ms / steps
+        return (self.max_over_ranks(ms) if collective else ms), int(launches)
+
+
+def measure_ffma_peak(ctx):
+    """FP32 FMA peak of THIS device, measured now: a pure FFMA stream (ured_probe_ffma), best of 5, CUDA events."""
+    import ctypes
+    torch = ctx.torch
+    sms = torch.cuda.get_device_properties(ctx.dev).multi_processor_count
+    sink = torch.zeros(16, device=ctx.dev)
+    flop = ctypes.c_double()
+    stream = torch.cuda.current_stream(ctx.dev).cuda_stream
+    best = None
+    for it in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.ured._native.check(ctx.lib.ured_probe_ffma(sink.data_ptr(), sms * 8, 4096, ctypes.byref(flop), stream), "ured_probe_ffma")
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if it >= 2:
+            best = ms if best is None else min(best, ms)
+    return flop.value / (best * 1e-3) / 1e12
+
+
+def nn_roofline(ctx, x_dev, gt_dev, B, n_x, n_gt, steps, warmup, exact_only, peaks, ffma_peak, workload):
+    """The dominant kernel alone: nn_kernel (both directions, one launch) on packed clouds, L2 flushed between launches."""
+    import ctypes
+    torch, ured, lib, dev = ctx.torch, ctx.ured, ctx.lib, ctx.dev
+    pk_gt, pk_x = ured.PackedClouds(gt_dev), ured.PackedClouds(x_dev)
+    d1 = torch.empty(B, n_gt, device=dev); d2 = torch.empty(B, n_x, device=dev)
+    i1 = torch.empty(B, n_gt, device=dev, dtype=torch.int32); i2 = torch.empty(B, n_x, device=dev, dtype=torch.int32)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    flags = 1 if exact_only else 0
+    scratch_bytes = lib.ured_nn_scratch_bytes(B, n_gt, n_x)
+    scratch = torch.empty(max(scratch_bytes, 256), dtype=torch.uint8, device=dev)
+
+    def nn_only():
+        rc = lib.ured_nn_packed(gt_dev.data_ptr(), pk_gt.packed.data_ptr(), n_gt,
+                                x_dev.data_ptr(), pk_x.packed.data_ptr(), n_x, B, 1, B, None, None,
+                                d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
+                                scratch.data_ptr(), scratch_bytes, flags, stream)
+        ured._native.check(rc, "ured_nn_packed")
+
+    ms_nn, _ = ctx.timed(nn_only, steps, warmup)
+    v, q, t, ns = (ctypes.c_int() for _ in range(4))
+    lib.ured_nn_launch_shape(B, n_gt, n_x, flags, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns))
+    pairs = 2.0 * B * n_x * n_gt
+    flop = FLOP_PER_PAIR * pairs
+    achieved = flop / (ms_nn * 1e-3) / 1e12
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_max_mhz = float(peaks.get("sm_max_mhz") or 1965.0)
+    peak = sms * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # FP32 FMA lanes x 2 FLOP x max SM clock
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "nn_kernel_traffic.json")))
+        traffic, traffic_src = tj.get(workload), tj.get("source")
+    except Exception:
+        pass
+    return {"bound": "fp32_fma", "kernel": "nn_kernel (both directions, one launch%s)" % (", + merge of %d candidate splits" % ns.value if ns.value > 1 else ""),
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 FLOP x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz; it has no FP32 figure)",
+            "measured_ffma_peak": ffma_peak, "frac_of_measured_ffma_peak": (achieved / ffma_peak) if ffma_peak else None,
+            "measured_ffma_peak_source": "ured_probe_ffma (pure FFMA stream) timed in this run, best of 5",
+            "flop_per_launch": flop, "kernel_ms": ms_nn, "tpair_per_s": pairs / (ms_nn * 1e-3) / 1e12,
+            "launch_shape": {"variant": v.value, "queries_per_cta": q.value, "threads": t.value, "candidate_splits": ns.value},
+            "note": "FLOP-accounted at the reference's 8 FLOP per ordered pair; the screening variant executes 6 FLOP per pair in its main loop "
+                    "(executed-FLOP fraction = 0.75 x frac)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# sharded library retrieval (cfg3 / cfg5): forward scoring + fused top-k / peer exchange / merge
+# ------------------------------------------------------------------------------------------------
+SLAB = 512   # the library is defined in global slabs of 512 shapes (seed = slab id): every world size sees the SAME library
+
+
+def library_rows(lo, hi, n, dev):
+    import torch
     slabs = []
     for sid in range(lo // SLAB, (hi + SLAB - 1) // SLAB if hi > lo else 0):
         x, _ = synth(SLAB, n, 8, seed=7000 + sid)
         a, b = max(lo, sid * SLAB) - sid * SLAB, min(hi, (sid + 1) * SLAB) - sid * SLAB
         slabs.append(x[a:b].to(dev))
-    shard = ured.PackedClouds(torch.cat(slabs)) if slabs else None
-    del slabs
-    _, tg_host = synth(Q, 8, n, seed=99)      # same targets on every rank
+    return torch.cat(slabs) if slabs else None
+
+
+def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, use_graph=True):
+    """One sharded-retrieval workload: every rank scores its shard of the library, ONE fused kernel exchanges and merges
+    the top-k.  Strong scaling.  Rank 0 also holds the whole library and produces, in the same run, the 1-rank time
+    and the 1-rank answer; the sharded ids must equal it (asserted) on every rank."""
+    import hashlib
+    torch, dist, ured, dev = ctx.torch, ctx.dist, ctx.ured, ctx.dev
+    S0, Q0, n, desc = RETRIEVAL[name]
+    S, Q, k = S or S0, Q or Q0, 10
+    heavy = 2.0 * Q * S * n * n > 5e11            # more than ~70 ms per step on one GPU: fewer steps
+    st_n, wu_n = (max(2, min(steps, 5)), 2) if heavy else (max(steps, 20), max(warmup, 5))
+    lo, hi = ured.shard_bounds(S, ctx.world, ctx.rank)
+    shard_x = library_rows(lo, hi, n, dev)
+    shard = ured.PackedClouds(shard_x) if shard_x is not None else None
+    _, tg_host = synth(Q, 8, n, seed=99)          # same targets on every rank
     tg_pin = tg_host.pin_memory()
     tg_dev = tg_pin.to(dev)
     out_s = torch.empty(Q, k).pin_memory()
     out_i = torch.empty(Q, k, dtype=torch.int32).pin_memory()
     pairs_per_step = 2.0 * Q * S * n * n
-
-    # one rank: CUDA-graph engine by default; several ranks: eager scoring + one all_gather (measured faster at 8 GPUs
-    # for single-query steps), graph incl. the collective on request
-    use_graph = (not args.eager) and (world == 1 or args.graph)
-    args.eager = not use_graph
-    engine = ured.RetrievalEngine(shard, lo, Q, k=k, metric="cd_t", use_graph=use_graph)
+    note = None
+    try:
+        engine = ured.RetrievalEngine(shard, lo, Q, k=k, metric="cd_t", use_graph=use_graph, exchange=exchange)
+        v, i = engine.query(tg_dev)
+        engine.check()
+    except ured.NativeLibraryError as exc:        # peer mapping refused on this box: time the NCCL exchange and say so
+        if exchange != "peer" or ctx.world == 1:
+            raise
+        note = f"peer mapping unavailable ({exc}); NCCL all_gather exchange timed instead"
+        exchange = "nccl"
+        engine = ured.RetrievalEngine(shard, lo, Q, k=k, metric="cd_t", use_graph=use_graph, exchange="nccl")
+        v, i = engine.query(tg_dev)
 
     def step_device():
         return engine.query(tg_dev)
 
     def step_e2e():
         t = tg_pin.to(dev, non_blocking=True)
-        v, i = engine.query(t)
-        out_s.copy_(v, non_blocking=True)
-        out_i.copy_(i, non_blocking=True)
+        vv, ii = engine.query(t)
+        out_s.copy_(vv, non_blocking=True)
+        out_i.copy_(ii, non_blocking=True)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup, sampler=None):
-        for _ in range(warmup):
-            fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        if sampler:
-            sampler.start()
-        l0 = lib.ured_kernel_launches()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        launches = lib.ured_kernel_launches() - l0
-        if sampler:
-            sampler.stop()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / steps, launches
-
-    sampler = ClockSampler(local_rank)
-    ms_step, launches = timed(step_device, args.steps, args.warmup, sampler)
-    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    ms_step, launches = ctx.timed(step_device, st_n, wu_n, flush=False)
+    ms_e2e, _ = ctx.timed(step_e2e, st_n, wu_n, flush=False)
     v, i = step_device()
+    engine.check()
     torch.cuda.synchronize()
-    line = {
-        "metric": "Chamfer+DCD fwd Gpair/s (sharded retrieval, top-k merged)", "value": pairs_per_step / (ms_step * 1e-3) / 1e9, "unit": UNIT,
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "library_shapes": S, "queries": Q, "points": n, "top_k": k,
-                   "shard": [lo, hi], "engine": "eager" if args.eager else ("cuda-graph" + ("" if world == 1 else " incl. all_gather")),
-                   "collective": "one all_gather of [Q,k] (score,id) pairs per step" if world > 1 else "none (1 rank)",
-                   "l2": "library shard (%.0f MB packed + raw) exceeds L2 except at the smallest sizes" % ((hi - lo) * n * 28 / 1e6)},
-        "e2e": {"value": pairs_per_step / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(tg_pin.numel() * 4), "d2h_bytes_per_step": int(Q * k * 8)},
-        "gpu_launches": int(launches) if args.eager else int(engine.kernels_per_replay * args.steps), "clocks": sampler.summary(),
-        "top1": {"score": float(v[0, 0]), "id": int(i[0, 0])},
-    }
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ids = i.cpu().contiguous()
+    sha = hashlib.sha1(ids.numpy().tobytes()).hexdigest()
+    rec = {"workload": f"{name}: {desc}", "library_shapes": S, "queries": Q, "points": n, "top_k": k, "n_gpus": ctx.world,
+           "scaling": "strong", "steps": st_n, "warmup": wu_n, "ms_per_step": ms_step,
+           "value": pairs_per_step / (ms_step * 1e-3) / 1e9, "unit": UNIT,
+           "e2e": {"ms_per_step": ms_e2e, "value": pairs_per_step / (ms_e2e * 1e-3) / 1e9, "h2d_bytes_per_step": int(tg_pin.numel() * 4),
+                   "d2h_bytes_per_step": int(Q * k * 8)},
+           "engine": "cuda-graph" if use_graph else "eager",
+           "exchange": ("none (1 rank)" if ctx.world == 1 else
+                        (f"fused top-k + peer stores + merge in one kernel ({engine.xchg.mapping})" if exchange == "peer"
+                         else "top-k kernel + NCCL all_gather + merge kernel")),
+           "kernels_per_step": engine.kernels_per_replay if use_graph else launches // max(st_n, 1),
+           "ids_sha1": sha, "top1": {"score": float(v[0, 0]), "id": int(i[0, 0])},
+           "l2": "library shard (%.0f MB packed + raw per rank) streamed every step; no flush needed above 126 MB, stated for smaller shards" % ((hi - lo) * n * 28 / 1e6)}
+    if note:
+        rec["note"] = note
+    # ---- the 1-rank answer and the 1-rank time, measured in this same run on rank 0 over the WHOLE library --------
+    if ctx.world > 1:
+        ctx.barrier()
+        one = {}
+        if ctx.rank == 0:
+            full = ured.PackedClouds(library_rows(0, S, n, dev))
+            e1 = ured.RetrievalEngine(full, 0, Q, k=k, metric="cd_t", use_graph=use_graph, exchange="peer")
+            e1.world, e1.exchange = 1, "none"          # a single-rank engine inside a multi-rank job
+            st_1, wu_1 = (2, 1) if heavy else (st_n, wu_n)
+            ms_1, _ = ctx.timed(lambda: e1.query(tg_dev), st_1, wu_1, flush=False, collective=False)
+            v1, i1 = e1.query(tg_dev)
+            torch.cuda.synchronize()
+            one = {"ms": ms_1, "sha": hashlib.sha1(i1.cpu().contiguous().numpy().tobytes()).hexdigest(), "steps": st_1,
+                   "scores_equal": bool(torch.equal(v1.cpu(), v.cpu()))}
+            del e1, full
+        box = [one]
+        dist.broadcast_object_list(box, src=0)
+        one = box[0]
+        shas = [None] * ctx.world
+        dist.all_gather_object(shas, sha)
+        rec["ms_per_step_1rank"] = one["ms"]
+        rec["steps_1rank"] = one["steps"]
+        rec["ids_sha1_1rank"] = one["sha"]
+        rec["ids_identical_on_all_ranks"] = all(s_ == sha for s_ in shas)
+        rec["ids_match_1rank"] = one["sha"] == sha
+        rec["scores_match_1rank"] = one["scores_equal"]
+        if not (rec["ids_identical_on_all_ranks"] and rec["ids_match_1rank"]):
+            raise SystemExit(f"bench.py: sharded retrieval {name} at {ctx.world} ranks does not reproduce the 1-rank ranking: {rec}")
+    else:
+        rec["ms_per_step_1rank"] = ms_step
+        rec["ids_sha1_1rank"] = sha
+        rec["ids_match_1rank"] = True
+    engine.close()
+    del engine, shard, shard_x
+    torch.cuda.empty_cache()
+    return rec
+
+
+# ------------------------------------------------------------------------------------------------
+# non-product leg: the reference's own CUDA op (recompiled for sm_100a, oracle/_ref) on this GPU
+# ------------------------------------------------------------------------------------------------
+def reference_cuda_leg(ctx, x_dev, gt_dev, pairs_per_step, ours_ms):
+    """time the UNMODIFIED reference op + the reference's torch-op calc_dcd body, fwd+bwd, same inputs."""
+    torch = ctx.torch
+    try:
+        from oracle import ref_cuda
+        ref = ref_cuda.load()
+        if ref is None:
+            return {"unavailable": "oracle/_ref not built on this box"}
+        fn = lambda: ref_cuda.calc_dcd_fwd_bwd(ref, x_dev, gt_dev, alpha=ALPHA, n_lambda=N_LAMBDA)  # noqa: E731
+        ms, _ = ctx.timed(fn, 10, 3, collective=False)
+        ms_fwd, _ = ctx.timed(lambda: ref_cuda.forward(ref, gt_dev, x_dev), 10, 3, collective=False)
+        return {"what": "unmodified chamfer3D.cu/chamfer_cuda.cpp built for sm_100a (oracle/_ref) + the reference's torch-op calc_dcd body, fwd+bwd; "
+                        "checker code timed as a yardstick, not part of the product path",
+                "ms": ms, "gpair_s": pairs_per_step / (ms * 1e-3) / 1e9, "forward_only_ms": ms_fwd,
+                "speedup": ms / ours_ms, "steps": 10, "warmup": 3, "l2": "256 MiB buffer rewritten between timed iterations"}
+    except Exception as exc:  # the checker is optional
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
+# ------------------------------------------------------------------------------------------------
+# the Chamfer+DCD fwd+bwd workloads (cfg2 headline; cfg1 / cfg4 as sub-records)
+# ------------------------------------------------------------------------------------------------
+def dcd_workload(ctx, wl, steps, warmup, exact_only, peaks, ffma_peak, sampler=None, with_e2e=True, with_graph=False):
+    torch, ured, dev = ctx.torch, ctx.ured, ctx.dev
+    B, n_x, n_gt, desc = WORKLOADS[wl]
+    pairs_per_step = 2.0 * B * n_x * n_gt
+    x_host, gt_host = synth(B, n_x, n_gt, seed=100 + ctx.rank)
+    if wl == "cfg2":  # one target per K=10 candidates: both arms see the same broadcast targets
+        gt_host = gt_host[::10].repeat_interleave(10, dim=0).contiguous()
+    x_pin, gt_pin = x_host.pin_memory(), gt_host.pin_memory()
+    x_dev, gt_dev = x_pin.to(dev), gt_pin.to(dev)
+
+    def step_device():
+        x = x_dev.detach().requires_grad_()
+        gt = gt_dev.detach().requires_grad_()
+        loss, _cd_p, _cd_t = ured.calc_dcd(x, gt, alpha=ALPHA, n_lambda=N_LAMBDA)
+        loss.sum().backward()
+        return loss, x.grad, gt.grad
+
+    ms_step, launches = ctx.timed(step_device, steps, warmup, sampler)
+    rec = {"workload": f"{wl}: {desc}", "pairs_per_gpu": B, "n_x": n_x, "n_gt": n_gt, "ms_per_step": ms_step,
+           "value": ctx.world * pairs_per_step / (ms_step * 1e-3) / 1e9, "gpu_launches": launches, "pairs_per_step": pairs_per_step}
+
+    if with_graph:
+        # the training-step form for repeated shapes: forward + unit-gradient backward captured once (graphed.GraphedDCD)
+        g = ured.GraphedDCD(B, n_x, n_gt, alpha=ALPHA, n_lambda=N_LAMBDA, device=dev)
+
+        def step_graph():
+            x = x_dev.detach().requires_grad_()
+            gt = gt_dev.detach().requires_grad_()
+            loss, _cd_p, _cd_t = g(x, gt)
+            loss.sum().backward()
+            return x.grad
+
+        ms_g, _ = ctx.timed(step_graph, steps, warmup)
+        rec["graph"] = {"ms_per_step": ms_g, "value": ctx.world * pairs_per_step / (ms_g * 1e-3) / 1e9,
+                        "what": "GraphedDCD: pack -> nn_kernel -> dcd_fwd_kernel -> grad kernel replayed as one CUDA graph, gradients scaled by the upstream g_loss"}
+
+    if with_e2e:
+        # ---- end to end: host buffers in, host result out, every step ---------------------------------
+        # Q targets [Q,N,3] and their K candidates [Q*K,M,3] sit in pinned host memory; each step copies BOTH to the device
+        # (copy stream, double buffered so that step i+1's upload overlaps step i's kernels, as a pinned-memory data loader
+        # does), broadcasts each target over its K candidates on the device, runs calc_dcd fwd+bwd and copies the per-pair
+        # loss back to pinned host memory.
+        K_CAND = 10 if (wl == "cfg2" and B % 10 == 0) else 1
+        gt_small_pin = gt_host[::K_CAND].contiguous().pin_memory()
+        loss_host = torch.empty(B, dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream(device=dev)
+        slots = [{"x": torch.empty_like(x_dev), "gt": torch.empty(B // K_CAND, n_gt, 3, device=dev), "ready": torch.cuda.Event(),
+                  "free": torch.cuda.Event()} for _ in range(2)]
+        state = {"i": 0, "primed": False}
+
+        def upload(slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(slot["free"])          # the step that last used this slot has finished reading it
+                slot["x"].copy_(x_pin, non_blocking=True)
+                slot["gt"].copy_(gt_small_pin, non_blocking=True)
+                slot["ready"].record(copy_stream)
+
+        def step_e2e():
+            cur = torch.cuda.current_stream(dev)
+            if not state["primed"]:
+                for sl in slots:
+                    sl["free"].record(cur)
+                upload(slots[0])
+                state["primed"] = True
+            slot = slots[state["i"] % 2]
+            upload(slots[(state["i"] + 1) % 2])               # prefetch the next step's inputs
+            cur.wait_event(slot["ready"])
+            x = slot["x"].detach().requires_grad_()
+            gt = slot["gt"].detach().repeat_interleave(K_CAND, dim=0).requires_grad_()
+            loss, _cd_p, _cd_t = ured.calc_dcd(x, gt, alpha=ALPHA, n_lambda=N_LAMBDA)
+            loss.sum().backward()
+            loss_host.copy_(loss.detach(), non_blocking=True)
+            slot["free"].record(cur)
+            state["i"] += 1
+            return x.grad
+
+        ms_e2e, _ = ctx.timed(step_e2e, steps, warmup, whole_loop=True)
+        torch.cuda.synchronize()
+        rec["e2e"] = {"value": ctx.world * pairs_per_step / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
+                      "h2d_bytes_per_step": int(x_pin.numel() * 4 + gt_small_pin.numel() * 4), "d2h_bytes_per_step": int(B * 4),
+                      "api": "pinned-host candidates + targets copied every step (copy stream, double-buffered), targets broadcast on device, "
+                             "calc_dcd fwd+bwd, per-pair loss copied back to pinned host"}
+    rec["roofline"] = nn_roofline(ctx, x_dev, gt_dev, B, n_x, n_gt, steps, warmup, exact_only, peaks, ffma_peak, wl)
+    rec["_inputs"] = (x_dev, gt_dev)
+    return rec
+
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
@@ -283,202 +544,82 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + sorted(RETRIEVAL))
-    ap.add_argument("--library-size", type=int, default=0, help="override S for the retrieval workloads")
-    ap.add_argument("--queries", type=int, default=0, help="override Q for the retrieval workloads")
-    ap.add_argument("--eager", action="store_true", help="retrieval workloads: eager calls instead of the CUDA-graph engine")
-    ap.add_argument("--graph", action="store_true", help="retrieval workloads on >1 rank: capture scoring + all_gather + merge in one CUDA graph")
+    ap.add_argument("--library-size", type=int, default=0, help="override S for a stand-alone retrieval workload")
+    ap.add_argument("--queries", type=int, default=0, help="override Q for a stand-alone retrieval workload")
+    ap.add_argument("--eager", action="store_true", help="retrieval: eager calls instead of the CUDA-graph engine")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="retrieval on >1 rank: fused peer-memory exchange or NCCL all_gather")
     ap.add_argument("--exact-only", action="store_true", help="disable the screening pass (difference form on every pair)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline workload: no cfg1/cfg4 sub-records, reference-op leg or retrieval record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
         run_reference_arm(args, args.workload if args.workload in WORKLOADS else "cfg2")
         return
-    if args.workload in RETRIEVAL:
-        run_retrieval(args)
-        return
 
-    import torch
-    import torch.distributed as dist
-    import ured_b200 as ured
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
-    lib = ured._native.load()
+    ctx = Ctx()
+    torch, dist = ctx.torch, ctx.dist
     if args.exact_only:
         os.environ["URED_EXACT_ONLY"] = "1"
-
-    B, n_x, n_gt, desc = WORKLOADS[args.workload]
-    pairs_per_step = 2.0 * B * n_x * n_gt
-    x_host, gt_host = synth(B, n_x, n_gt, seed=100 + rank)
-    if args.workload == "cfg2":  # one target per K=10 candidates: both arms see the same broadcast targets
-        gt_host = gt_host[::10].repeat_interleave(10, dim=0).contiguous()
-    x_pin, gt_pin = x_host.pin_memory(), gt_host.pin_memory()
-    x_dev, gt_dev = x_pin.to(dev), gt_pin.to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def step_device():
-        x = x_dev.detach().requires_grad_()
-        gt = gt_dev.detach().requires_grad_()
-        loss, _cd_p, _cd_t = ured.calc_dcd(x, gt, alpha=ALPHA, n_lambda=N_LAMBDA)
-        loss.sum().backward()
-        return loss, x.grad, gt.grad
-
-    # ---- end to end: host buffers in, host result out, every step ---------------------------------
-    # The retrieval workload's natural host-side form: Q=64 targets [Q,N,3] and their K=10 candidates
-    # [Q*K,M,3] sit in pinned host memory; each step copies BOTH to the device (copy stream, double
-    # buffered so that step i+1's upload overlaps step i's kernels, as a pinned-memory data loader does),
-    # broadcasts each target over its K candidates on the device, runs calc_dcd fwd+bwd and copies the
-    # per-pair loss back to pinned host memory.
-    K_CAND = 10 if B % 10 == 0 else 1
-    gt_small_pin = gt_host[::K_CAND].contiguous().pin_memory()
-    loss_host = torch.empty(B, dtype=torch.float32).pin_memory()
-    copy_stream = torch.cuda.Stream(device=dev)
-    slots = [{"x": torch.empty_like(x_dev), "gt": torch.empty(B // K_CAND, n_gt, 3, device=dev), "ready": torch.cuda.Event(),
-              "free": torch.cuda.Event()} for _ in range(2)]
-    state = {"i": 0, "primed": False}
-
-    def upload(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(slot["free"])          # the step that last used this slot has finished reading it
-            slot["x"].copy_(x_pin, non_blocking=True)
-            slot["gt"].copy_(gt_small_pin, non_blocking=True)
-            slot["ready"].record(copy_stream)
-
-    def step_e2e():
-        cur = torch.cuda.current_stream(dev)
-        if not state["primed"]:
-            for sl in slots:
-                sl["free"].record(cur)
-            upload(slots[0])
-            state["primed"] = True
-        slot = slots[state["i"] % 2]
-        upload(slots[(state["i"] + 1) % 2])               # prefetch the next step's inputs
-        cur.wait_event(slot["ready"])
-        x = slot["x"].detach().requires_grad_()
-        gt = slot["gt"].detach().repeat_interleave(K_CAND, dim=0).requires_grad_()
-        loss, _cd_p, _cd_t = ured.calc_dcd(x, gt, alpha=ALPHA, n_lambda=N_LAMBDA)
-        loss.sum().backward()
-        loss_host.copy_(loss.detach(), non_blocking=True)
-        slot["free"].record(cur)
-        state["i"] += 1
-        return x.grad
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup, sampler=None, whole_loop=False):
-        for _ in range(warmup):
-            fn()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(1 if whole_loop else steps)]
-        barrier()
-        if sampler:
-            sampler.start()
-        launches0 = lib.ured_kernel_launches()
-        if whole_loop:
-            # copies for step i+1 overlap step i, so the loop is bracketed once (no untimed gaps to hide work in);
-            # every step's inputs arrive fresh from the host, so there is no L2 flush here
-            ev[0][0].record()
-            for s in range(steps):
-                fn()
-            ev[0][1].record()
-        else:
-            for s in range(steps):
-                flush.zero_()          # evict L2 between timed iterations (outside the event pair)
-                ev[s][0].record()
-                fn()
-                ev[s][1].record()
-        barrier()
-        launches = lib.ured_kernel_launches() - launches0
-        if sampler:
-            sampler.stop()
-        total_ms = sum(a.elapsed_time(b) for a, b in ev)
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / steps, launches
-
-    sampler = ClockSampler(local_rank)
-    ms_step, launches = timed(step_device, args.steps, args.warmup, sampler)
-    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup, whole_loop=True)
-    torch.cuda.synchronize()
-
-    # ---- dominant kernel alone: nn_kernel (both directions, one launch) on packed clouds ---------
-    pk_gt, pk_x = ured.PackedClouds(gt_dev), ured.PackedClouds(x_dev)
-    d1 = torch.empty(B, n_gt, device=dev); d2 = torch.empty(B, n_x, device=dev)
-    i1 = torch.empty(B, n_gt, device=dev, dtype=torch.int32); i2 = torch.empty(B, n_x, device=dev, dtype=torch.int32)
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    flags = 1 if args.exact_only else 0
-
-    scratch_bytes = lib.ured_nn_scratch_bytes(B, n_gt, n_x)
-    scratch = torch.empty(max(scratch_bytes, 256), dtype=torch.uint8, device=dev)
-
-    def nn_only():
-        rc = lib.ured_nn_packed(gt_dev.data_ptr(), pk_gt.packed.data_ptr(), n_gt,
-                                x_dev.data_ptr(), pk_x.packed.data_ptr(), n_x, B, 1, B, None, None,
-                                d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
-                                scratch.data_ptr(), scratch_bytes, flags, stream)
-        ured._native.check(rc, "ured_nn_packed")
-
-    ms_nn, _ = timed(nn_only, args.steps, args.warmup)
-    flop_per_launch = FLOP_PER_PAIR * pairs_per_step
-    achieved_tflops = flop_per_launch / (ms_nn * 1e-3) / 1e12
-
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    sm_max_mhz = float(peaks.get("sm_max_mhz") or sampler.max_mhz or 1965.0)
-    peak_tflops = sms * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # FP32 FMA lanes x 2 FLOP x max SM clock
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "nn_kernel_traffic.json"))).get(args.workload)
-    except Exception:
-        pass
 
+    if args.workload in RETRIEVAL:   # stand-alone retrieval run (development): its record is the line
+        rec = retrieval_record(ctx, args.workload, args.steps, args.warmup, exchange=args.exchange, S=args.library_size or None,
+                               Q=args.queries or None, use_graph=not args.eager)
+        if ctx.rank == 0:
+            print(json.dumps(rec), flush=True)
+        if ctx.world > 1:
+            dist.destroy_process_group()
+        return
+
+    ffma_peak = measure_ffma_peak(ctx)
+    sampler = ClockSampler(ctx.local_rank)
+    wl = args.workload
+    main_rec = dcd_workload(ctx, wl, args.steps, args.warmup, args.exact_only, peaks, ffma_peak, sampler=sampler)
+    x_dev, gt_dev = main_rec.pop("_inputs")
+    B, n_x, n_gt, desc = WORKLOADS[wl]
     line = {
-        "metric": METRIC, "value": world * pairs_per_step / (ms_step * 1e-3) / 1e9, "unit": UNIT,
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "metric": METRIC, "value": main_rec["value"], "unit": UNIT,
+        "n_gpus": ctx.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_rec["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "pairs_per_gpu": B, "n_x": n_x, "n_gt": n_gt, "alpha": ALPHA,
-                   "n_lambda": N_LAMBDA, "step": "calc_dcd fwd + loss.sum().backward()", "sharding": "independent pairs per rank, no collective",
+        "config": {"workload": main_rec["workload"], "pairs_per_gpu": B, "n_x": n_x, "n_gt": n_gt, "alpha": ALPHA,
+                   "n_lambda": N_LAMBDA, "step": "calc_dcd fwd + loss.sum().backward()", "sharding": "independent pairs per rank, no collective "
+                   "(the sharded workload with its exchange is the `retrieval` record)",
                    "kernel_variant": "exact-only" if args.exact_only else "screen+exact-recheck",
                    "l2": "256 MiB buffer rewritten between timed iterations"},
-        "e2e": {"value": world * pairs_per_step / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(x_pin.numel() * 4 + gt_small_pin.numel() * 4), "d2h_bytes_per_step": int(B * 4),
-                "api": "pinned-host candidates + targets copied every step (copy stream, double-buffered), targets broadcast on device, "
-                       "calc_dcd fwd+bwd, per-pair loss copied back to pinned host"},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "fp32_fma", "kernel": "nn_kernel (both directions, one launch)", "achieved": achieved_tflops,
-                     "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops, "traffic": traffic,
-                     "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 FLOP x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz; it has no FP32 figure); "
-                                    "tools/microbench/fp32_peak.cu measured 72.6 (FFMA) / 74.3 (FFMA2) TFLOP/s on this pool",
-                     "frac_of_measured_ffma_peak": achieved_tflops / 72.6,  # profiles/r01_microbench_fp32_peak.txt (scalar FFMA stream)
-                     "flop_per_launch": flop_per_launch, "kernel_ms": ms_nn,
-                     "tpair_per_s": pairs_per_step / (ms_nn * 1e-3) / 1e12,
-                     "note": "FLOP-accounted at the reference's 8 FLOP per ordered pair; the screening variant executes 6 FLOP per pair in its main loop"},
-        "clocks": sampler.summary(),
+        "e2e": main_rec["e2e"], "gpu_launches": main_rec["gpu_launches"], "roofline": main_rec["roofline"], "clocks": sampler.summary(),
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if not args.no_extras:
+        if ctx.world == 1:
+            # the other single-GPU configurations of BASELINE.json, each with its own roofline
+            subs = {}
+            for name in ("cfg1", "cfg4"):
+                if name == wl:
+                    continue
+                r = dcd_workload(ctx, name, max(10, min(args.steps, 30)), args.warmup, args.exact_only, peaks, ffma_peak,
+                                 with_e2e=False, with_graph=(name == "cfg1"))
+                r.pop("_inputs")
+                subs[name] = r
+                torch.cuda.empty_cache()
+            line["configs"] = subs
+            line["reference_cuda_op"] = reference_cuda_leg(ctx, x_dev, gt_dev, main_rec["pairs_per_step"], main_rec["ms_per_step"])
+        del x_dev, gt_dev
+        torch.cuda.empty_cache()
+        retr = {}
+        for name in ("cfg3", "cfg5"):
+            retr[name] = retrieval_record(ctx, name, args.steps, args.warmup, exchange=args.exchange)
+        line["retrieval"] = retr
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
         sample_pairs = 32 if n_x * n_gt <= 2048 * 2048 else 1
         line["cpu_baseline"] = {k: v for k, v in cpu_baseline(n_x, n_gt, sample_pairs, 3, 1).items() if k != "sec_per_step"}
-    if rank == 0:
+    if ctx.rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if ctx.world > 1:
         dist.destroy_process_group()
 
 

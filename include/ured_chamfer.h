@@ -21,7 +21,8 @@
  *
  * Conventions (all entry points)
  *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
- *     (the library never allocates or frees device memory; its only global state is a launch counter);
+ *     (the library never allocates or frees device memory -- the one exception is the peer-exchange buffer of
+ *     ured_xchg_alloc, which must be an exportable cudaMalloc block; its only global state is a launch counter);
  *   - clouds are row-major contiguous float32 [count, n, 3]; distances float32; indices int32
  *     (same dtypes as the reference: dist_chamfer_3D.py:33-37);
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it
@@ -94,6 +95,9 @@ int ured_pack_clouds(const float *xyz, int count, int n, const int *len, void *p
  * several CTAs and merged afterwards; that needs `scratch`: ured_nn_scratch_bytes(B, n1, n2) bytes (0 for most
  * shapes, in which case scratch may be NULL), 256-byte aligned. */
 size_t ured_nn_scratch_bytes(int B, int n1, int n2);
+/* The launch shape ured_nn_packed will use for this problem (reporting / tests): kernel variant id, queries per CTA,
+ * threads per CTA and the number of candidate splits.  Any output pointer may be NULL. */
+int ured_nn_launch_shape(int B, int n1, int n2, unsigned flags, int *variant, int *queries_per_cta, int *threads, int *nsplit);
 int ured_nn_packed(const float *xyz1, const void *packed1, int n1,
                    const float *xyz2, const void *packed2, int n2,
                    int B, int rep1, int mod2, const int *len1, const int *len2,
@@ -129,7 +133,23 @@ int ured_chamfer_backward(const float *xyz1, const float *xyz2, int B, int n1, i
  *          w1_i = frac_21 / (count1[idx1_i]^n_lambda + 1e-6), count1 = histogram of idx1
  *          over the n2 points of cloud 2; symmetric for w2 with frac_12     model_utils.py:31-45
  * ew1 [B, n1] / ew2 [B, n2] (optional, may be NULL) receive exp(-alpha d) * w per point, the
- * only per-point state the backward pass needs.  Sums are accumulated in float64. */
+ * only per-point state the backward pass needs.
+ *
+ * Reduction order.  The per-pair means are accumulated in float32 in the order of torch's own reduction kernel for a
+ * contiguous [B >= 16, n] tensor (one warp per row, 4-wide vector slots, shuffle-down tree; ATen Reduce.cuh), for
+ * 128 < n < 8192, so that loss / cd_p / cd_t carry the same bits as the reference's `.mean(1)` calls on the same
+ * dist/idx and a ranking cannot differ by a last-bit swap (tests/test_gpu_ranking.py holds this against torch).
+ * Outside that range, and for ragged pairs, the order is still fixed (results are deterministic) but torch picks a
+ * different block shape, so agreement is to float32 round-off only.
+ *
+ * ured_dcd_forward_ex additionally fills fscore [3, B] (f-score, precision_1, precision_2 at `f_threshold`,
+ * metrics/CD/fscore.py:3-16; NULL to skip); loss/cd_p/cd_t/ew may each be NULL. */
+int ured_dcd_forward_ex(const float *dist1, const float *dist2, const int *idx1, const int *idx2,
+                        int B, int n1, int n2, int rep1, int mod2, const int *len1, const int *len2,
+                        float alpha, float n_lambda, float frac_12, float frac_21, unsigned flags,
+                        float *loss, float *cd_p, float *cd_t, float *ew1, float *ew2,
+                        float *fscore, float f_threshold, void *stream);
+/* the same without the F-score outputs */
 int ured_dcd_forward(const float *dist1, const float *dist2, const int *idx1, const int *idx2,
                      int B, int n1, int n2, int rep1, int mod2, const int *len1, const int *len2,
                      float alpha, float n_lambda, float frac_12, float frac_21, unsigned flags,
@@ -161,6 +181,43 @@ int ured_topk_smallest(const float *scores, int rows, int cols, int k, int idx_o
  * fewer than k real entries the tail is (+inf, -1). */
 int ured_merge_topk(const float *scores, const int *ids, int rows, int cols, int k,
                     float *out_scores, int *out_ids, void *stream);
+
+/* ---- measurement aid ------------------------------------------------------------------------------------------------
+ * Launches a pure FFMA stream (8 independent chains per thread, blocks x 256 threads, 64 FFMA per iteration) and
+ * reports its FLOP count; bench.py times it with CUDA events to obtain the FP32 FMA peak of the device it runs on. */
+int ured_probe_ffma(float *sink, int blocks, int iters, double *flop, void *stream);
+
+/* ---- sharded retrieval: fused local top-k + peer exchange + merge ---------------------------------------------------
+ * The library is split over `world` ranks (one process per GPU); every rank scores its shard and needs the global k
+ * best (score, shape id) per query.  The reference has no counterpart (it is single-GPU: engine/generate_pair.py:69-122
+ * ranks with torch.topk, dataset/dataset_utils.py:1043-1051); SURVEY.md 8(e) defines the exchange.  Instead of
+ * "top-k kernel, NCCL all_gather, merge kernel" ONE kernel selects the local top-k, stores it into every peer's
+ * exchange buffer over NVLink, publishes a flag, waits for the peers' flags in its own buffer and merges.
+ *
+ * Set-up (once): every rank allocates a buffer of ured_xchg_bytes(world, rows, k) with ured_xchg_alloc, exports a
+ * 64-byte handle, the handles travel over any side channel (torch.distributed all_gather in this package), every
+ * rank imports the others' handles and passes the table bufs[world] (own buffer at [rank]) to ured_topk_exchange.
+ * Any other peer mapping of buffers of that size (zero-initialised) works as well, e.g. torch symmetric memory.
+ * This buffer is the only device memory the library ever allocates (it must be a whole cudaMalloc block to be
+ * exportable).  Limits: world <= 16, rows <= 512 per call (all CTAs of a call wait for their peers while resident),
+ * k <= 64.  All ranks must issue the same sequence of ured_topk_exchange calls with the same rows / k.
+ * A peer that does not arrive within timeout_ms (0 = 5000) makes the call write ids = -2 and set the buffer's status
+ * word (ured_xchg_status) instead of hanging the GPU. */
+#define URED_XCHG_HANDLE_BYTES 64
+size_t ured_xchg_bytes(int world, int rows, int k);
+int ured_xchg_alloc(size_t bytes, void **dev_ptr);
+int ured_xchg_free(void *dev_ptr);
+int ured_xchg_export(void *dev_ptr, void *handle64);
+int ured_xchg_import(const void *handle64, void **peer_ptr);
+int ured_xchg_close(void *peer_ptr);
+/* synchronises `stream`; status 0 = every exchange so far completed, 1 = some exchange timed out */
+int ured_xchg_status(const void *own_buf, int *status, unsigned *epoch, void *stream);
+/* scores [rows, cols] of this rank's shard (column c = shape id c + idx_offset) -> out_scores / out_ids [rows, k]:
+ * the k smallest over ALL ranks in ascending (score, id) order, identical on every rank; (+inf, -1) pads a library
+ * of fewer than k shapes.  cols may be 0 (an empty shard still takes part in the exchange). */
+int ured_topk_exchange(const float *scores, int rows, int cols, int k, int idx_offset,
+                       void *const *bufs, int world, int rank, int buf_rows,
+                       float *out_scores, int *out_ids, unsigned timeout_ms, void *stream);
 
 #ifdef __cplusplus
 }

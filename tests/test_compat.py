@@ -44,3 +44,26 @@ def test_reference_caller_files_import_unmodified(installed):
     import torch
     with pytest.raises(RuntimeError, match="GPU tensors only"):   # the reference's code reaches our op (no CPU fallback)
         mod.chamfer_distance2(torch.rand(1, 8, 3), torch.rand(1, 8, 3))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the authoring container")
+def test_aliases_win_with_the_reference_root_on_sys_path(ured):
+    """INTEGRATION.md's flow: the reference root is on sys.path, so the genuine DCD package is importable -- the aliases
+    must still take over (otherwise engine/geometry_utils.py would JIT-build and run the reference's CUDA op)."""
+    before = dict(sys.modules)
+    sys.path.insert(0, REF)
+    try:
+        names = ured.compat.install()
+        assert "Density_aware_Chamfer_Distance.utils_v2.model_utils" in names and "Shape_Measure.distance" in names
+        from Density_aware_Chamfer_Distance.utils_v2.model_utils import calc_dcd
+        from Density_aware_Chamfer_Distance.utils_v2.metrics import cd
+        import Density_aware_Chamfer_Distance
+        assert calc_dcd is ured.calc_dcd and cd is ured.chamfer_3DDist
+        # the alias package still finds the genuine package's other submodules on disk
+        assert any(p.startswith(REF) for p in Density_aware_Chamfer_Distance.__path__)
+        assert importlib.util.find_spec("Density_aware_Chamfer_Distance.models") is not None
+    finally:
+        sys.path.remove(REF)
+        for n in list(sys.modules):
+            if n not in before:
+                del sys.modules[n]

@@ -7,6 +7,12 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+import sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+from helpers_merge import cpu_merge  # noqa: E402  (tests/helpers_merge.py: the reference merge used by the CPU tests)
+
 
 def test_shard_bounds_cover_library(ured):
     for S in [0, 1, 7, 8, 125, 1000, 100003]:
@@ -17,7 +23,12 @@ def test_shard_bounds_cover_library(ured):
             assert max(hi - lo for lo, hi in spans) == (S + world - 1) // world
 
 
-def test_merge_topk_is_lexicographic(ured, oracle):
+def test_product_merge_has_no_cpu_path(ured):
+    with pytest.raises(RuntimeError, match="GPU tensors only"):
+        ured.merge_topk(torch.zeros(1, 3), torch.zeros(1, 3, dtype=torch.int32), 2)
+
+
+def test_reference_merge_is_lexicographic(ured, oracle):
     g = torch.Generator().manual_seed(0)
     scores = torch.rand(5, 1000, generator=g).round(decimals=2)  # heavy ties
     k = 10
@@ -26,12 +37,12 @@ def test_merge_topk_is_lexicographic(ured, oracle):
         lo, hi = ured.shard_bounds(1000, 8, r)
         s, i = oracle.t.topk_oracle(scores[:, lo:hi], k)
         cols.append((s, i + lo))
-    ms, mi = ured.merge_topk(torch.cat([c[0] for c in cols], 1), torch.cat([c[1] for c in cols], 1), k)
+    ms, mi = cpu_merge(torch.cat([c[0] for c in cols], 1), torch.cat([c[1] for c in cols], 1), k)
     ws, wi = oracle.t.topk_oracle(scores, k)
     assert torch.equal(mi, wi) and torch.equal(ms, ws)
     # padding entries (id -1) never surface
     s = torch.tensor([[0.5, 0.1, 9.0]]); i = torch.tensor([[4, 2, -1]], dtype=torch.int32)
-    ms, mi = ured.merge_topk(s, i, 3)
+    ms, mi = cpu_merge(s, i, 3)
     assert mi.tolist() == [[2, 4, -1]] and ms[0, 2] == float("inf")
 
 
@@ -40,6 +51,8 @@ def _worker(rank, world, port, tmp):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import ured_b200 as ured
     from oracle import torch_path
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers_merge import cpu_merge
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -49,7 +62,7 @@ def _worker(rank, world, port, tmp):
         k = 10
         lo, hi = ured.shard_bounds(37, world, rank)
         ls, li = torch_path.topk_oracle(scores[:, lo:hi], min(k, hi - lo))
-        ms, mi = ured.gather_and_merge(ls, (li + lo).int(), k)
+        ms, mi = ured.gather_and_merge(ls, (li + lo).int(), k, merge=cpu_merge)
         ws, wi = torch_path.topk_oracle(scores, k)
         ok = torch.equal(mi, wi) and torch.equal(ms, ws)
         torch.save({"ok": ok, "ids": mi}, os.path.join(tmp, f"r{rank}.pt"))
