@@ -39,6 +39,7 @@ _SIGNATURES = {
     "ured_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
     "ured_chamfer_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _u, _p]),
     "ured_chamfer_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ured_nn_backward_one_direction": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "ured_dcd_forward": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _f, _f, _f, _f, _u, _p, _p, _p, _p, _p, _p]),
     "ured_dcd_forward_ex": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _f, _f, _f, _f, _u, _p, _p, _p, _p, _p, _p, _f, _p]),
     "ured_dcd_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -56,14 +56,25 @@ def compute_cm_loss(source_p, target_p, target_part, mask=None, batch_reduction=
         return full.mean(), full.new_zeros(())
     if src.shape[1] < P * 1024:
         raise ValueError("source_p has fewer than 1024 points per target part")
-    m_max = max(t.shape[0] for tp in target_part for t in tp)
-    tgt = src.new_zeros(B * P, m_max, 3)
-    len_tgt = torch.zeros(B * P, dtype=torch.int32)
+    # Padded [B*P, m_max, 3] targets from the ragged parts with a fixed number of device operations -- one cat, one
+    # scatter -- whatever B and P are (the row / column of every point is computed on the host from the shapes alone).
+    import numpy as np
+    sizes = np.zeros(B * P, dtype=np.int64)
+    pieces = []
     for bs, tp in enumerate(target_part):
         for i, t in enumerate(tp):
-            tgt[bs * P + i, :t.shape[0]] = t
-            len_tgt[bs * P + i] = t.shape[0]
-    len_tgt = len_tgt.to(dev)
+            sizes[bs * P + i] = t.shape[0]
+            if t.shape[0]:
+                pieces.append(t)
+    m_max = int(sizes.max())
+    if m_max == 0:
+        return full.mean(), full.new_zeros(())
+    flat = torch.cat(pieces).to(device=dev, dtype=src.dtype)                        # [sum(sizes), 3]
+    row_of = np.repeat(np.arange(B * P, dtype=np.int64), sizes)
+    col_of = np.arange(int(sizes.sum()), dtype=np.int64) - np.repeat(np.cumsum(sizes) - sizes, sizes)
+    where = torch.from_numpy(row_of * m_max + col_of).to(dev, non_blocking=True)    # one H2D copy
+    tgt = src.new_zeros(B * P * m_max, 3).index_copy_(0, where, flat).view(B * P, m_max, 3)
+    len_tgt = torch.from_numpy(sizes.astype(np.int32)).to(dev, non_blocking=True)
     parts_src = src[:, :P * 1024].reshape(B * P, 1024, 3)
     _, _, per_part, _, _, _, _ = chamfer_ragged(parts_src, tgt, len_gt=len_tgt, alpha=0.0)
     present = (len_tgt > 0).view(B, P).to(per_part.dtype)

@@ -369,18 +369,21 @@ __global__ void __launch_bounds__(T, MINB) nn_kernel(const NNParams p) {
     if (SCREEN) cn = __fsqrt_ru(csoa[(size_t)ncp_max * 4]) * 1.000001f;  // max W of the candidate cloud (block tail)
     const int lane = tid & 31;
     const int rot = lane & 7;  // 16-byte piece this lane starts its chunk at (see below)
-    // One query per iteration, always from element 0 of the register arrays, which are then shifted down by one: the
-    // loop stays rolled (the re-check is ~400 instructions; unrolled R times it would not fit the instruction cache)
-    // without ever indexing a register array dynamically.
+    // U queries per iteration (unrolled: their dependent compare chains interleave), always elements 0..U-1 of the register
+    // arrays, which are then shifted down by U: for R > U the loop stays rolled (the re-check is ~400 instructions per
+    // query; unrolled 16 times it would not fit the instruction cache) without ever indexing a register array dynamically.
+    constexpr int U = R < 4 ? R : 4;
 #pragma unroll 1
-    for (int it = 0; it < R; it++) {
-        const float oqx = kUnscale * qx[0], oqy = kUnscale * qy[0], oqz = kUnscale * qz[0];
-        const int c = min(bchunk[0], ncp - G);  // (an empty trailing split re-reads the last chunk; its result loses every merge)
+    for (int it = 0; it < R; it += U) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const float oqx = kUnscale * qx[u], oqy = kUnscale * qy[u], oqz = kUnscale * qz[u];
+        const int c = min(bchunk[u], ncp - G);  // (an empty trailing split re-reads the last chunk; its result loses every merge)
         // Exact difference form on the chunk's G candidates (packed math, same bits as exact_d).  Entries past nc
         // replicate point nc-1, so they can tie with it but sit at higher indices and never win.
         const float nq1 = SCREEN ? 0.5f : 1.0f;  // registers hold -2q (SCREEN) or -q (EXACT); both rescalings are exact
-        const float2 nqx = make_float2(nq1 * qx[0], nq1 * qx[0]), nqy = make_float2(nq1 * qy[0], nq1 * qy[0]),
-                     nqz = make_float2(nq1 * qz[0], nq1 * qz[0]);
+        const float2 nqx = make_float2(nq1 * qx[u], nq1 * qx[u]), nqy = make_float2(nq1 * qy[u], nq1 * qy[u]),
+                     nqz = make_float2(nq1 * qz[u], nq1 * qz[u]);
         // d >= +0 for every finite pair, so the running minimum is kept on the float's bit pattern (same order)
         unsigned bdu = 0u;
         int bi = c;
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(T, MINB) nn_kernel(const NNParams p) {
             const float qn = __fsqrt_ru(__fmaf_rn(oqz, oqz, __fmaf_rn(oqy, oqy, oqx * oqx))) * 1.000001f;
             const float S = qn + cn;
             const float eps = __fmaf_rn(S * S, 1.9073486e-6f /* 2^-19 */, 1e-35f);
-            const bool ambiguous = !(second[0] > best[0] + eps);
+            const bool ambiguous = !(second[u] > best[u] + eps);
             unsigned todo = __ballot_sync(0xffffffffu, ambiguous);
             while (todo) {
                 const int src = __ffs(todo) - 1;
@@ -463,18 +466,21 @@ __global__ void __launch_bounds__(T, MINB) nn_kernel(const NNParams p) {
                 if (lane == src) { bd = wd; bi = wi; }
             }
         }
-        const int j = (qt * R + it) * T + tid;
+        const int j = (qt * R + it + u) * T + tid;
         if (j < nq) {
             if (j >= nq_v) { bd = 0.0f; bi = 0; }                          // past the valid length of a ragged cloud
             else if (p.nsplit > 1 && k_lo >= k_hi) bd = kInf;              // empty split: loses every merge
             out_d[j] = bd;
             out_i[j] = bi;
         }
+      }
+      if (R > U) {
 #pragma unroll
-        for (int r = 0; r + 1 < R; r++) {
-            qx[r] = qx[r + 1]; qy[r] = qy[r + 1]; qz[r] = qz[r + 1];
-            best[r] = best[r + 1]; second[r] = second[r + 1]; bchunk[r] = bchunk[r + 1];
+        for (int r = 0; r + U < R; r++) {
+            qx[r] = qx[r + U]; qy[r] = qy[r + U]; qz[r] = qz[r + U];
+            best[r] = best[r + U]; second[r] = second[r + U]; bchunk[r] = bchunk[r + U];
         }
+      }
     }
 }
 
@@ -711,6 +717,7 @@ struct GradParams {
     int rep1, mod2;
     float alpha;
     const int *len[2];  // optional valid point counts per cloud-1 / cloud-2 entry
+    int one_dir;        // only cloud-1 points searched cloud 2 (K=1 kNN): cloud-2 points have no term of their own
 };
 __device__ __forceinline__ int valid_len(const int *len, size_t cloud, int n_max) {
     return len ? max(0, min(len[cloud], n_max)) : n_max;
@@ -734,7 +741,7 @@ __global__ void __launch_bounds__(kGradThreads) grad_kernel(const GradParams p) 
         const size_t pt = b * n_own + j;
         const int v_own = valid_len(side ? p.len[1] : p.len[0], c_own, n_own);
         const int v_oth = valid_len(side ? p.len[0] : p.len[1], c_oth, n_oth);
-        if (j >= v_own || v_oth == 0) {  // past the valid length (or nothing to match): zero gradient
+        if (j >= v_own || v_oth == 0 || (side && p.one_dir)) {  // past the valid length, nothing to match, or no search from this side: zero gradient
             if (PHASE == 0 && !(side ? SHARED2 : SHARED1)) {
                 float *dst = (side ? p.grad[1] : p.grad[0]) + (c_own * n_own + j) * 3;
                 dst[0] = 0.0f; dst[1] = 0.0f; dst[2] = 0.0f;
@@ -765,10 +772,17 @@ __global__ void __launch_bounds__(kGradThreads) grad_kernel(const GradParams p) 
     }
 }
 
-// One CTA per pair, both clouds' gradients accumulated in shared memory (own-side and scatter-side
-// terms alike), then written out once, coalesced: no global atomics, no zero-fill, one launch.
-// Used when the pair's (n1 + n2) * 12 bytes fit in shared memory and neither cloud is broadcast.
+// One CTA per pair, atomic-free and bit-reproducible.  The scatter side of the reference's backward
+// (grad_xyz2[idx1[i]] -= g_i (p1_i - p2_idx), chamfer3D.cu:168-172, six float atomics per point) is turned into a
+// gather: a counting sort of the argmin indices gives, for every point j, the list of points of the other cloud that
+// chose j; each list is put in ascending order and summed by ONE thread, so the result does not depend on any
+// scheduling (the reference's atomics and a shared-memory CAS loop both do).  Everything lives in shared memory:
+//   vec[(n1+n2)*3]  every point's own term g (p_own - p_nn)
+//   seg[n2 | n1]    segment ends after the counting sort (bins = points of the cloud being pointed AT)
+//   lst[n1 | n2]    the pointing points, grouped by the point they chose
+// Used when the pair fits (20 bytes per point) and neither cloud is broadcast over several pairs.
 constexpr int kGradSmemThreads = 512;
+constexpr int kGradSortMax = 32;  // longer lists (adversarial clouds: many points choosing one) are rebuilt by a linear scan
 
 __device__ __forceinline__ float point_grad_coeff(const GradParams &p, int side, size_t b, size_t pt, int n_own) {
     const float *g_dist = side ? p.g_dist[1] : p.g_dist[0];
@@ -779,48 +793,119 @@ __device__ __forceinline__ float point_grad_coeff(const GradParams &p, int side,
     return gd;
 }
 
-__global__ void __launch_bounds__(kGradSmemThreads) grad_smem_kernel(const GradParams p) {
-    extern __shared__ float acc[];  // grad of cloud 1 [n1*3] | grad of cloud 2 [n2*3]
+// in-place exclusive prefix sum of a[0..n) by the whole CTA (kGradSmemThreads threads); scratch: 33 ints
+__device__ __forceinline__ void block_exclusive_scan(int *a, int n, int *scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + kGradSmemThreads - 1) / kGradSmemThreads;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    int sum = 0;
+    for (int k = lo; k < hi; k++) sum += a[k];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < kGradSmemThreads / 32 ? scratch[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += y;
+        }
+        scratch[lane] = winc - w;  // exclusive offset of each warp
+    }
+    __syncthreads();
+    int run = scratch[warp] + inc - sum;
+    for (int k = lo; k < hi; k++) { const int t = a[k]; a[k] = run; run += t; }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kGradSmemThreads) grad_gather_kernel(const GradParams p) {
+    extern __shared__ float gsm[];
+    __shared__ int scan_scratch[33];
     const size_t b = blockIdx.x;
-    const int n1 = p.n[0], n2 = p.n[1];
+    const int tid = threadIdx.x;
+    const int n1 = p.n[0], n2 = p.n[1], nt = n1 + n2;
+    float *vec = gsm;                                   // [nt * 3]
+    int *seg = reinterpret_cast<int *>(gsm + nt * 3);   // [n2 | n1]: bins of side-1 lists (points of cloud 2), then of side-2 lists
+    int *lst = seg + nt;                                // [n1 | n2]
     const float *xyz1 = p.xyz[0] + b * n1 * 3, *xyz2 = p.xyz[1] + b * n2 * 3;
+    const int *idx1 = p.idx[0] + b * n1, *idx2 = p.idx[1] + b * n2;
     const int v1 = valid_len(p.len[0], b, n1), v2 = valid_len(p.len[1], b, n2);
-    // Shared-memory float atomicAdd is a CAS loop on sm_100 (ATOMS.CAST.SPIN), so only the scatter side uses it:
-    // phase 0 STORES every point's own-side term (which also initialises the accumulators), phase 1 adds the
-    // scatter-side terms atomically.  The per-point term is recomputed in phase 1 (its loads hit L1).
-#pragma unroll 1
-    for (int phase = 0; phase < 2; phase++) {
-        for (int t = threadIdx.x; t < n1 + n2; t += kGradSmemThreads) {
-            const int side = t >= n1 ? 1 : 0;
-            const int j = side ? t - n1 : t;
+    const bool live = v1 > 0 && v2 > 0;  // an empty side: no matches, zero gradients
+
+    // ---- 1. histogram of the argmins (bins = the points being chosen) ----------------------------------------------
+    for (int k = tid; k < nt; k += kGradSmemThreads) seg[k] = 0;
+    __syncthreads();
+    if (live) {
+        for (int i = tid; i < v1; i += kGradSmemThreads) atomicAdd(&seg[idx1[i]], 1);          // integer shared atomics are native
+        if (!p.one_dir)
+            for (int i = tid; i < v2; i += kGradSmemThreads) atomicAdd(&seg[n2 + idx2[i]], 1);
+    }
+    __syncthreads();
+    // ---- 2. segment starts ------------------------------------------------------------------------------------------
+    block_exclusive_scan(seg, n2, scan_scratch);
+    block_exclusive_scan(seg + n2, n1, scan_scratch);
+    // ---- 3. own terms + grouping: pos = seg[bin]++ leaves seg[bin] = END of the bin's segment ------------------------
+    for (int t = tid; t < nt; t += kGradSmemThreads) {
+        const int side = t >= n1 ? 1 : 0;
+        const int j = side ? t - n1 : t;
+        float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+        if (live && j < (side ? v2 : v1) && !(side && p.one_dir)) {
             const int n_own = side ? n2 : n1;
-            float *own = acc + (side ? n1 * 3 : 0) + j * 3;
-            if (j >= (side ? v2 : v1) || (side ? v1 : v2) == 0) {
-                if (phase == 0) { own[0] = 0.0f; own[1] = 0.0f; own[2] = 0.0f; }
-                continue;
-            }
             const size_t pt = b * n_own + j;
             const float gd = point_grad_coeff(p, side, b, pt, side ? v2 : v1);
-            const int j2 = (side ? p.idx[1] : p.idx[0])[pt];
+            const int j2 = side ? idx2[j] : idx1[j];
             const float *a = (side ? xyz2 : xyz1) + j * 3;
             const float *o = (side ? xyz1 : xyz2) + j2 * 3;
             const float g = __fmul_rn(gd, 2.0f);  // chamfer3D.cu:166
-            const float gx = __fmul_rn(g, __fsub_rn(a[0], o[0]));
-            const float gy = __fmul_rn(g, __fsub_rn(a[1], o[1]));
-            const float gz = __fmul_rn(g, __fsub_rn(a[2], o[2]));
-            if (phase == 0) {
-                own[0] = gx; own[1] = gy; own[2] = gz;
-            } else {
-                float *oth = acc + (side ? 0 : n1 * 3) + j2 * 3;
-                atomicAdd(oth + 0, -gx); atomicAdd(oth + 1, -gy); atomicAdd(oth + 2, -gz);
-            }
+            gx = __fmul_rn(g, __fsub_rn(a[0], o[0]));
+            gy = __fmul_rn(g, __fsub_rn(a[1], o[1]));
+            gz = __fmul_rn(g, __fsub_rn(a[2], o[2]));
+            const int pos = atomicAdd(&seg[(side ? n2 : 0) + j2], 1);
+            lst[(side ? n1 : 0) + pos] = j;
         }
-        if (phase == 0) __syncthreads();
+        vec[t * 3 + 0] = gx; vec[t * 3 + 1] = gy; vec[t * 3 + 2] = gz;
     }
     __syncthreads();
-    float *g1 = p.grad[0] + b * n1 * 3, *g2 = p.grad[1] + b * n2 * 3;
-    for (int k = threadIdx.x; k < n1 * 3; k += kGradSmemThreads) g1[k] = acc[k];
-    for (int k = threadIdx.x; k < n2 * 3; k += kGradSmemThreads) g2[k] = acc[n1 * 3 + k];
+    // ---- 4. gather: point j of cloud c sums its own term and, in ascending index order, minus the terms of the points
+    //         of the other cloud that chose it -------------------------------------------------------------------------
+    for (int t = tid; t < nt; t += kGradSmemThreads) {
+        const int side = t >= n1 ? 1 : 0;          // the cloud this point belongs to
+        const int j = side ? t - n1 : t;
+        // points of the OTHER cloud pointing at j: side-0 points are chosen by cloud-2 points (lists of side 1) and vice versa
+        const int *sg = side ? seg : seg + n2;     // bins over this cloud's points
+        int *ls = side ? lst : lst + n1;           // lists of the other cloud's points
+        const float *ov = side ? vec : vec + n1 * 3;
+        const int start = j == 0 ? 0 : sg[j - 1], end = sg[j];
+        const int len = end - start;
+        float ax = vec[t * 3 + 0], ay = vec[t * 3 + 1], az = vec[t * 3 + 2];
+        if (len <= kGradSortMax) {
+            for (int u = start + 1; u < end; u++) {             // insertion sort of a short, thread-private segment
+                const int key = ls[u];
+                int w = u - 1;
+                while (w >= start && ls[w] > key) { ls[w + 1] = ls[w]; w--; }
+                ls[w + 1] = key;
+            }
+            for (int u = start; u < end; u++) {
+                const int i = ls[u];
+                ax = __fsub_rn(ax, ov[i * 3 + 0]); ay = __fsub_rn(ay, ov[i * 3 + 1]); az = __fsub_rn(az, ov[i * 3 + 2]);
+            }
+        } else {
+            const int *oidx = side ? idx1 : idx2;               // ascending scan of the other cloud's argmins
+            const int n_oth = side ? v1 : v2;
+            for (int i = 0; i < n_oth; i++)
+                if (oidx[i] == j) { ax = __fsub_rn(ax, ov[i * 3 + 0]); ay = __fsub_rn(ay, ov[i * 3 + 1]); az = __fsub_rn(az, ov[i * 3 + 2]); }
+        }
+        // straight to global memory (consecutive threads write consecutive 12-byte triples); vec keeps the own terms,
+        // which other threads are still reading
+        float *dst = (side ? p.grad[1] + b * n2 * 3 : p.grad[0] + b * n1 * 3) + j * 3;
+        dst[0] = ax; dst[1] = ay; dst[2] = az;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1080,6 +1165,8 @@ int check_pairs(int B, int n1, int n2, int rep1, int mod2) {
 inline int count1_of(int B, int rep1) { return (B + rep1 - 1) / rep1; }
 inline int count2_of(int B, int mod2) { return B < mod2 ? B : mod2; }
 
+inline bool flags_env_general() { return env_int("URED_GRAD_GENERAL", 0) != 0; }  // tests: force the global-atomic backward
+
 template <bool SCREEN, int R, int T, int MINB>
 int launch_nn(const NNParams &p, int B, cudaStream_t st) {
     constexpr int NARR = SCREEN ? 4 : 3;
@@ -1294,7 +1381,8 @@ int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n
     if (n1 == 0 || n2 == 0 || shared1) { if (n1) URED_CUDA(cudaMemsetAsync(gradxyz1, 0, (size_t)cnt1 * n1 * 12, st), "memset"); }
     if (n1 == 0 || n2 == 0 || shared2) { if (n2) URED_CUDA(cudaMemsetAsync(gradxyz2, 0, (size_t)cnt2 * n2 * 12, st), "memset"); }
     if (n1 == 0 || n2 == 0) return 0;
-    if (!xyz1 || !xyz2 || !idx1 || !idx2) return fail_arg(URED_E_NULL, "ured_dcd_backward: NULL input");
+    if (!xyz1 || !xyz2 || !idx1) return fail_arg(URED_E_NULL, "ured_dcd_backward: NULL input");
+    if (!idx2 && (g_dist2 || g_loss || g_cd_p || g_cd_t)) return fail_arg(URED_E_NULL, "ured_dcd_backward: NULL idx2 (only the one-direction backward may omit it)");
     if (g_loss && (!ew1 || !ew2)) return fail_arg(URED_E_NULL, "ured_dcd_backward: g_loss needs ew1/ew2");
     if (g_cd_p && (!dist1 || !dist2)) return fail_arg(URED_E_NULL, "ured_dcd_backward: g_cd_p needs dist1/dist2");
     GradParams p;
@@ -1309,13 +1397,14 @@ int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n
     p.rep1 = rep1; p.mod2 = mod2;
     p.alpha = alpha;
     p.len[0] = len1; p.len[1] = len2;
-    const size_t smem_need = (size_t)(n1 + n2) * 3 * sizeof(float);
-    if (!shared1 && !shared2 && smem_need <= 96 * 1024) {
+    p.one_dir = idx2 ? 0 : 1;   // (ured_nn_backward_one_direction passes no idx2)
+    const size_t smem_need = (size_t)(n1 + n2) * 20;  // own terms (12 B) + segment ends (4 B) + lists (4 B) per point
+    if (!shared1 && !shared2 && smem_need <= 200 * 1024 && !(flags_env_general())) {
         if (smem_need > 48 * 1024)
-            URED_CUDA(cudaFuncSetAttribute(grad_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "grad smem attribute");
-        grad_smem_kernel<<<B, kGradSmemThreads, smem_need, st>>>(p);
+            URED_CUDA(cudaFuncSetAttribute(grad_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "grad smem attribute");
+        grad_gather_kernel<<<B, kGradSmemThreads, smem_need, st>>>(p);
         URED_COUNT_LAUNCH();
-        return check_cuda(cudaGetLastError(), "grad_smem_kernel launch");
+        return check_cuda(cudaGetLastError(), "grad_gather_kernel launch");
     }
     int gx = (n1 + n2 + kGradThreads - 1) / kGradThreads;
     if (gx > 64) gx = 64;
@@ -1337,6 +1426,12 @@ int ured_chamfer_backward(const float *xyz1, const float *xyz2, int B, int n1, i
                           float *gradxyz1, float *gradxyz2, void *stream) {
     return ured_dcd_backward(xyz1, xyz2, B, n1, n2, rep1, mod2, len1, len2, nullptr, nullptr, idx1, idx2, nullptr, nullptr, 0.0f, nullptr,
                              nullptr, nullptr, graddist1, graddist2, gradxyz1, gradxyz2, stream);
+}
+
+int ured_nn_backward_one_direction(const float *xyz1, const float *xyz2, int B, int n1, int n2, const int *len2,
+                                   const float *graddist1, const int *idx1, float *gradxyz1, float *gradxyz2, void *stream) {
+    return ured_dcd_backward(xyz1, xyz2, B, n1, n2, 1, B > 0 ? B : 1, nullptr, len2, nullptr, nullptr, idx1, nullptr, nullptr, nullptr, 0.0f,
+                             nullptr, nullptr, nullptr, graddist1, nullptr, gradxyz1, gradxyz2, stream);
 }
 
 int ured_topk_smallest(const float *scores, int rows, int cols, int k, int idx_offset, float *out_scores, int *out_idx,

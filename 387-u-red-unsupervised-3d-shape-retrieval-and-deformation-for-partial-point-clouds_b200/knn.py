@@ -9,7 +9,7 @@ import torch
 from torch.autograd import Function
 
 from . import _native
-from .dist_chamfer_3D import _len_arg, _require_cloud, _stream, nn_backward
+from .dist_chamfer_3D import _len_arg, _require_cloud, _stream
 
 
 class _NearestOne(Function):
@@ -43,8 +43,15 @@ class _NearestOne(Function):
         p1, p2, idx1 = ctx.saved_tensors
         if g_dist is None:
             return None, None, None
-        idx2 = torch.zeros(p2.shape[0], p2.shape[1], device=p2.device, dtype=torch.int32)
-        g1, g2 = nn_backward(p1, p2, g_dist.contiguous().float(), None, idx1, idx2, len2=ctx.len2)
+        lib = _native.load()
+        B, n1, _ = p1.shape
+        n2 = p2.shape[1]
+        g_dist = g_dist.contiguous().float()
+        g1, g2 = torch.empty_like(p1), torch.empty_like(p2)
+        with torch.cuda.device(p1.device):   # cloud-2 points have no term of their own: only the scatter side runs for them
+            rc = lib.ured_nn_backward_one_direction(_native.ptr(p1), _native.ptr(p2), B, n1, n2, _native.ptr(ctx.len2), _native.ptr(g_dist),
+                                                    _native.ptr(idx1), _native.ptr(g1), _native.ptr(g2), _stream(p1.device))
+        _native.check(rc, "ured_nn_backward_one_direction")
         return g1, g2, None
 
 

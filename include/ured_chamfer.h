@@ -124,6 +124,12 @@ int ured_chamfer_backward(const float *xyz1, const float *xyz2, int B, int n1, i
                           const int *idx1, const int *idx2,
                           float *gradxyz1, float *gradxyz2, void *stream);
 
+/* Backward of the one-direction search (ured_nn_packed with URED_FLAG_ONE_DIRECTION; K=1 knn_points of
+ * loss/basic_loss.py:249-265): only cloud-1 points carry a distance, so cloud-2 points get the scatter terms alone. */
+int ured_nn_backward_one_direction(const float *xyz1, const float *xyz2, int B, int n1, int n2, const int *len2,
+                                   const float *graddist1, const int *idx1,
+                                   float *gradxyz1, float *gradxyz2, void *stream);
+
 /* ---- calc_cd / calc_dcd epilogue ------------------------------------------------------------
  * From (dist1, idx1) [B, n1] and (dist2, idx2) [B, n2] of chamfer(gt, x) -- note the
  * reference's argument swap, model_utils.py:56: cloud 1 = gt, cloud 2 = x -- computes per pair
