@@ -486,18 +486,31 @@ __global__ void __launch_bounds__(T, MINB) nn_kernel(const NNParams p) {
 
 // Merge of the per-split partial results: splits cover ascending candidate ranges, so a strict '<' in split
 // order keeps the lowest index among equal distances -- the same rule as the reference's tile merge (chamfer3D.cu:126).
-__global__ void __launch_bounds__(256) merge_splits_kernel(const float *__restrict__ pd, const int *__restrict__ pi, size_t total,
-                                                           int nsplit, float *__restrict__ dist, int *__restrict__ idx) {
-    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+// One launch covers both directions: elements [0, total1) belong to direction 0, the rest to direction 1.
+struct MergeParams {
+    const float *pd[2];
+    const int *pi[2];
+    float *dist[2];
+    int *idx[2];
+    size_t total[2];
+    int nsplit;
+};
+__global__ void __launch_bounds__(256) merge_splits_kernel(const MergeParams m) {
+    size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const int dir = t >= m.total[0] ? 1 : 0;
+    if (dir) t -= m.total[0];
+    const size_t total = dir ? m.total[1] : m.total[0];
     if (t >= total) return;
+    const float *__restrict__ pd = dir ? m.pd[1] : m.pd[0];
+    const int *__restrict__ pi = dir ? m.pi[1] : m.pi[0];
     float d = pd[t];
     int i = pi[t];
-    for (int s = 1; s < nsplit; s++) {
+    for (int s = 1; s < m.nsplit; s++) {
         const float ds = pd[s * total + t];
         if (ds < d) { d = ds; i = pi[s * total + t]; }
     }
-    dist[t] = d;
-    idx[t] = i;
+    (dir ? m.dist[1] : m.dist[0])[t] = d;
+    (dir ? m.idx[1] : m.idx[0])[t] = i;
 }
 
 // Launch shape: a kernel variant (T threads x R queries per thread, MINB resident CTAs per SM) and nsplit candidate
@@ -512,7 +525,7 @@ struct NNVariant { int R, T, minb; };
 constexpr int kNumVariants = 8;
 const NNVariant kVariants[kNumVariants] = {
     {4, 128, 5},   // 0: default
-    {4, 128, 4},   // 1
+    {4, 128, 6},   // 1
     {8, 128, 3},   // 2
     {8, 64, 6},    // 3
     {16, 64, 4},   // 4
@@ -573,8 +586,10 @@ struct DcdLens { const int *len1, *len2; int rep1, mod2, non_reg; };
 // last-bit swap.  ATen reduces a contiguous fp32 row of a [rows >= 16, n] tensor with a 32-lane warp per row
 // (block 32 x 16, 4-wide vector loads): lane t owns the 16-byte vectors t, t+32, ... with one accumulator per vector
 // slot, an unaligned head / a tail of n % 4 elements go to slot 0 of the lanes that own them, the four slots are
-// added left to right, and the lanes are combined by shuffle-down with offsets 1, 2, 4, 8, 16
-// (aten/src/ATen/native/cuda/Reduce.cuh: input_vectorized_thread_reduce_impl, block_x_reduce).  `f(k)` is the k-th
+// added left to right, and the lanes are combined by shuffle-down with offsets 16, 8, 4, 2, 1
+// (aten/src/ATen/native/cuda/Reduce.cuh: input_vectorized_thread_reduce_impl, block_x_reduce; the schedule was
+// identified against torch 2.11 on a B200 with tools/diag_torch_reduce.py -- of ten candidate orders this is the only
+// one that reproduces torch's sums on every row, profiles/r02_diag_torch_reduce.txt).  `f(k)` is the k-th
 // element of the row, `mis` the row's misalignment in elements ((address / 4) % 4).  Result valid in lane 0.
 template <typename F>
 __device__ __forceinline__ float torch_row_sum(F f, int n, int mis, int lane) {
@@ -595,7 +610,7 @@ __device__ __forceinline__ float torch_row_sum(F f, int n, int mis, int lane) {
     }
     float v = __fadd_rn(__fadd_rn(__fadd_rn(acc0, acc1), acc2), acc3);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, o));
     return v;
 }
 
@@ -1042,31 +1057,42 @@ __global__ void __launch_bounds__(kXchgThreads) topk_exchange_kernel(const XchgP
     const int slot = (int)(epoch & 1u);
     if (tid == 0) timed_out = 0u;
 
-    // ---- 1. local top-k of this row: k passes, each the block-wide minimum of the keys above the previous pick ----
+    // ---- 1. local top-k of this row ----------------------------------------------------------------------------------
     const float *srow = p.scores + (size_t)row * p.cols;
-    unsigned long long last = 0ull;
-    for (int it = 0; it < k; it++) {
-        unsigned long long m = ~0ull;
+    if (p.cols <= kXchgMaxWorld * kXchgMaxK) {
+        // short rows (a small shard): every key's rank by counting the keys below it -- one pass, no k-fold reduction
+        unsigned long long *keys = all_keys;   // (free until the merge)
+        for (int c = tid; c < p.cols; c += kXchgThreads) keys[c] = score_key(srow[c], c + p.idx_offset);
+        for (int j = p.cols + tid; j < k; j += kXchgThreads) mine[j] = ~0ull;   // fewer than k shapes: padding, sorts last
+        __syncthreads();
         for (int c = tid; c < p.cols; c += kXchgThreads) {
-            const unsigned long long key = score_key(srow[c], c + p.idx_offset);
-            if ((it == 0 || key > last) && key < m) m = key;
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
-            if (other < m) m = other;
-        }
-        if ((tid & 31) == 0) red[tid >> 5] = m;
-        __syncthreads();
-        if (tid == 0) {
-            for (int i = 1; i < kXchgThreads / 32; i++) if (red[i] < m) m = red[i];
-            mine[it] = m;  // ~0 when the shard holds fewer than k shapes: padding, sorts last
+            const unsigned long long key = keys[c];
+            int below = 0;
+            for (int u = 0; u < p.cols; u++) below += keys[u] < key ? 1 : 0;   // ids are unique -> keys are unique
+            if (below < k) mine[below] = key;
         }
         __syncthreads();
-        last = mine[it];
-        if (last == ~0ull) {  // exhausted: the rest is padding
-            for (int j = it + 1 + tid; j < k; j += kXchgThreads) mine[j] = ~0ull;
+    } else {
+        // long rows: k passes, each the block-wide minimum of the keys above the previous pick
+        unsigned long long last = 0ull;
+        for (int it = 0; it < k; it++) {
+            unsigned long long m = ~0ull;
+            for (int c = tid; c < p.cols; c += kXchgThreads) {
+                const unsigned long long key = score_key(srow[c], c + p.idx_offset);
+                if ((it == 0 || key > last) && key < m) m = key;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
+                if (other < m) m = other;
+            }
+            if ((tid & 31) == 0) red[tid >> 5] = m;
             __syncthreads();
-            break;
+            if (tid == 0) {
+                for (int i = 1; i < kXchgThreads / 32; i++) if (red[i] < m) m = red[i];
+                mine[it] = m;
+            }
+            __syncthreads();
+            last = mine[it];
         }
     }
 
@@ -1183,7 +1209,7 @@ int launch_nn_variant(int variant, bool exact, const NNParams &p, int B, cudaStr
     if (exact) return (variant == 5) ? launch_nn<false, 2, 128, 6>(p, B, st) : launch_nn<false, 4, 128, 5>(p, B, st);
     switch (variant) {
         case 0: return launch_nn<true, 4, 128, 5>(p, B, st);
-        case 1: return launch_nn<true, 4, 128, 4>(p, B, st);
+        case 1: return launch_nn<true, 4, 128, 6>(p, B, st);
         case 2: return launch_nn<true, 8, 128, 3>(p, B, st);
         case 3: return launch_nn<true, 8, 64, 6>(p, B, st);
         case 4: return launch_nn<true, 16, 64, 4>(p, B, st);
@@ -1290,12 +1316,15 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
     }
     rc = launch_nn_variant(sh.variant, exact, p, B, st);
     if (rc || sh.nsplit == 1) return rc;
-    merge_splits_kernel<<<(unsigned)((tot1 + 255) / 256), 256, 0, st>>>(p.part_dist[0], p.part_idx[0], tot1, sh.nsplit, dist1, idx1);
+    MergeParams mp;
+    mp.pd[0] = p.part_dist[0]; mp.pd[1] = p.part_dist[1];
+    mp.pi[0] = p.part_idx[0]; mp.pi[1] = p.part_idx[1];
+    mp.dist[0] = dist1; mp.dist[1] = dist2;
+    mp.idx[0] = idx1; mp.idx[1] = idx2;
+    mp.total[0] = tot1; mp.total[1] = one_dir ? 0 : tot2;
+    mp.nsplit = sh.nsplit;
+    merge_splits_kernel<<<(unsigned)((mp.total[0] + mp.total[1] + 255) / 256), 256, 0, st>>>(mp);
     URED_COUNT_LAUNCH();
-    if (!one_dir) {
-        merge_splits_kernel<<<(unsigned)((tot2 + 255) / 256), 256, 0, st>>>(p.part_dist[1], p.part_idx[1], tot2, sh.nsplit, dist2, idx2);
-        URED_COUNT_LAUNCH();
-    }
     return check_cuda(cudaGetLastError(), "merge_splits_kernel launch");
 }
 
