@@ -526,9 +526,9 @@ constexpr int kNumVariants = 8;
 const NNVariant kVariants[kNumVariants] = {
     {4, 128, 5},   // 0: default
     {4, 128, 6},   // 1
-    {8, 128, 3},   // 2
-    {8, 64, 6},    // 3
-    {16, 64, 4},   // 4
+    {8, 128, 4},   // 2
+    {8, 64, 8},    // 3
+    {6, 128, 4},   // 4
     {2, 128, 6},   // 5: smallest tile (256 queries) for launches that cannot fill the machine otherwise
     {8, 128, 2},   // 6
     {4, 64, 8},    // 7
@@ -621,17 +621,23 @@ struct DcdOut {
     int B;
 };
 
+// STAGED: the per-point terms are computed by ALL threads (independent, unrolled loads: memory-level parallelism), staged
+// in shared memory next to the histograms, and the six ordered row sums then run over shared memory.  Needs 8 bytes per
+// point; pairs too large for that (more than 25 600 points) compute the terms inside the ordered sums instead.
+template <bool STAGED>
 __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__restrict__ dist1, const float *__restrict__ dist2,
                                                               const int *__restrict__ idx1, const int *__restrict__ idx2,
                                                               int n1_max, int n2_max, float alpha, float n_lambda, float frac_12,
                                                               float frac_21, const DcdOut out, const DcdLens lens) {
-    extern __shared__ int hist[];  // count1[n2] | count2[n1]
+    extern __shared__ int hist[];  // count1[n2] | count2[n1]   (STAGED: later reused for d1 | d2)   then term1[n1] | term2[n2]
     __shared__ float sums[8];
     int *count1 = hist, *count2 = hist + n2_max;
+    const int nt_max = n1_max + n2_max;
+    float *term = reinterpret_cast<float *>(hist + nt_max);   // STAGED only
     const size_t b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float *d1 = dist1 + b * n1_max, *d2 = dist2 + b * n2_max;
-    const int *i1 = idx1 + b * n1_max, *i2 = idx2 + b * n2_max;
+    const float *__restrict__ d1 = dist1 + b * n1_max, *__restrict__ d2 = dist2 + b * n2_max;
+    const int *__restrict__ i1 = idx1 + b * n1_max, *__restrict__ i2 = idx2 + b * n2_max;
     const bool ragged = lens.len1 || lens.len2;
     const int n1 = lens.len1 ? max(0, min(lens.len1[b / lens.rep1], n1_max)) : n1_max;
     const int n2 = lens.len2 ? max(0, min(lens.len2[b % lens.mod2], n2_max)) : n2_max;
@@ -653,10 +659,38 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
     }
     const bool want_loss = out.loss || out.ew1 || out.ew2;
     if (want_loss) {
-        for (int k = tid; k < n1_max + n2_max; k += kDcdThreads) hist[k] = 0;
+        for (int k = tid; k < nt_max; k += kDcdThreads) hist[k] = 0;
         __syncthreads();
+#pragma unroll 4
         for (int k = tid; k < n1; k += kDcdThreads) atomicAdd(&count1[i1[k]], 1);
+#pragma unroll 4
         for (int k = tid; k < n2; k += kDcdThreads) atomicAdd(&count2[i2[k]], 1);
+        __syncthreads();
+    }
+    // model_utils.py:31,35-37: exp(-d*alpha); (count**lambda + 1e-6)**(-1) * frac; the term is 1 - e*w
+    auto ew_of = [&](float dk, int c, float frac) {
+        const float e = expf(__fmul_rn(-dk, alpha));
+        const float w = __fmul_rn(__fdiv_rn(1.0f, __fadd_rn(pow_lambda((float)c, n_lambda), 1e-6f)), frac);
+        return __fmul_rn(e, w);
+    };
+    if (STAGED) {
+        if (want_loss) {
+#pragma unroll 4
+            for (int t = tid; t < nt_max; t += kDcdThreads) {
+                const int side = t >= n1_max ? 1 : 0;
+                const int k = side ? t - n1_max : t;
+                const bool valid = k < (side ? n2 : n1);
+                float ewk = 0.0f;
+                if (valid) ewk = ew_of(side ? d2[k] : d1[k], side ? count2[i2[k]] : count1[i1[k]], side ? frac_12 : frac_21);
+                float *ew = side ? out.ew2 : out.ew1;
+                if (ew) ew[b * (side ? n2_max : n1_max) + k] = ewk;   // (zero past the valid length of a ragged cloud)
+                term[t] = __fsub_rn(1.0f, ewk);
+            }
+            __syncthreads();   // every count has been read: the histogram space now takes the distances
+        }
+        float *sd = reinterpret_cast<float *>(hist);
+#pragma unroll 4
+        for (int t = tid; t < nt_max; t += kDcdThreads) sd[t] = t >= n1_max ? d2[t - n1_max] : d1[t];
         __syncthreads();
     }
 
@@ -670,28 +704,33 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
     const int *cnt = side ? count2 : count1;
     const float frac = side ? frac_12 : frac_21;
     float *ew = side ? out.ew2 : out.ew1;
-    const int mis = ragged ? 0 : (int)((reinterpret_cast<uintptr_t>(d) >> 2) & 3u);  // (a ragged pair stands for a per-sample call: aligned)
+    // the row's misalignment decides which elements torch's kernel treats as the unaligned head (a ragged pair stands for
+    // a per-sample call: aligned)
+    const int mis = ragged ? 0 : (int)((reinterpret_cast<uintptr_t>(d) >> 2) & 3u);
+    const float *sdist = reinterpret_cast<const float *>(hist) + (side ? n1_max : 0);   // STAGED: distances in shared memory
+    const float *sterm = term + (side ? n1_max : 0);
     float r = 0.0f;
     if (what == 0) {
         if (want_loss) {
-            // model_utils.py:31,35-37: exp(-d*alpha); (count**lambda + 1e-6)**(-1) * frac; the term is 1 - e*w
-            auto term = [&](int k) {
-                const float e = expf(__fmul_rn(-d[k], alpha));
-                const float w = __fmul_rn(__fdiv_rn(1.0f, __fadd_rn(pow_lambda((float)cnt[ix[k]], n_lambda), 1e-6f)), frac);
-                const float ewk = __fmul_rn(e, w);
-                if (ew) ew[b * n_stride + k] = ewk;
-                return __fsub_rn(1.0f, ewk);
-            };
-            r = torch_row_sum(term, n, mis, lane);
-            if (ew) for (int k = n + lane; k < n_stride; k += 32) ew[b * n_stride + k] = 0.0f;
+            if (STAGED) {
+                r = torch_row_sum([&](int k) { return sterm[k]; }, n, mis, lane);
+            } else {
+                r = torch_row_sum([&](int k) {
+                        const float ewk = ew_of(d[k], cnt[ix[k]], frac);
+                        if (ew) ew[b * n_stride + k] = ewk;
+                        return __fsub_rn(1.0f, ewk);
+                    }, n, mis, lane);
+                if (ew) for (int k = n + lane; k < n_stride; k += 32) ew[b * n_stride + k] = 0.0f;
+            }
         }
     } else if (what == 1) {
-        r = torch_row_sum([&](int k) { return d[k]; }, n, mis, lane);
+        r = STAGED ? torch_row_sum([&](int k) { return sdist[k]; }, n, mis, lane) : torch_row_sum([&](int k) { return d[k]; }, n, mis, lane);
     } else if (what == 2) {
-        r = torch_row_sum([&](int k) { return sqrtf(d[k]); }, n, mis, lane);
+        r = STAGED ? torch_row_sum([&](int k) { return sqrtf(sdist[k]); }, n, mis, lane)
+                   : torch_row_sum([&](int k) { return sqrtf(d[k]); }, n, mis, lane);
     } else if (out.fscore) {
         int c = 0;
-        for (int k = lane; k < n; k += 32) c += d[k] < out.f_threshold ? 1 : 0;
+        for (int k = lane; k < n; k += 32) c += (STAGED ? sdist[k] : d[k]) < out.f_threshold ? 1 : 0;
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         r = (float)c;  // a sum of 0/1 floats is exact in any order
     }
@@ -857,34 +896,59 @@ __global__ void __launch_bounds__(kGradSmemThreads) grad_gather_kernel(const Gra
     for (int k = tid; k < nt; k += kGradSmemThreads) seg[k] = 0;
     __syncthreads();
     if (live) {
+#pragma unroll 4
         for (int i = tid; i < v1; i += kGradSmemThreads) atomicAdd(&seg[idx1[i]], 1);          // integer shared atomics are native
-        if (!p.one_dir)
+        if (!p.one_dir) {
+#pragma unroll 4
             for (int i = tid; i < v2; i += kGradSmemThreads) atomicAdd(&seg[n2 + idx2[i]], 1);
+        }
     }
     __syncthreads();
     // ---- 2. segment starts ------------------------------------------------------------------------------------------
     block_exclusive_scan(seg, n2, scan_scratch);
     block_exclusive_scan(seg + n2, n1, scan_scratch);
     // ---- 3. own terms + grouping: pos = seg[bin]++ leaves seg[bin] = END of the bin's segment ------------------------
-    for (int t = tid; t < nt; t += kGradSmemThreads) {
-        const int side = t >= n1 ? 1 : 0;
-        const int j = side ? t - n1 : t;
-        float gx = 0.0f, gy = 0.0f, gz = 0.0f;
-        if (live && j < (side ? v2 : v1) && !(side && p.one_dir)) {
-            const int n_own = side ? n2 : n1;
-            const size_t pt = b * n_own + j;
-            const float gd = point_grad_coeff(p, side, b, pt, side ? v2 : v1);
-            const int j2 = side ? idx2[j] : idx1[j];
-            const float *a = (side ? xyz2 : xyz1) + j * 3;
-            const float *o = (side ? xyz1 : xyz2) + j2 * 3;
-            const float g = __fmul_rn(gd, 2.0f);  // chamfer3D.cu:166
-            gx = __fmul_rn(g, __fsub_rn(a[0], o[0]));
-            gy = __fmul_rn(g, __fsub_rn(a[1], o[1]));
-            gz = __fmul_rn(g, __fsub_rn(a[2], o[2]));
-            const int pos = atomicAdd(&seg[(side ? n2 : 0) + j2], 1);
-            lst[(side ? n1 : 0) + pos] = j;
+    // Four points per thread and step, in two sweeps: first every independent load (argmin, own coordinates, upstream
+    // coefficient), then the dependent gathers of the chosen points -- the step is bound by memory latency, so what
+    // matters is how many loads are in flight, not how many instructions run.
+    constexpr int U = 4;
+    for (int base = 0; base < nt; base += kGradSmemThreads * U) {
+        int j2[U];
+        float gd[U], ax[U], ay[U], az[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int t = base + u * kGradSmemThreads + tid;
+            const int side = t >= n1 ? 1 : 0;
+            const int j = side ? t - n1 : t;
+            ok[u] = t < nt && live && j < (side ? v2 : v1) && !(side && p.one_dir);
+            j2[u] = 0; gd[u] = 0.0f; ax[u] = ay[u] = az[u] = 0.0f;
+            if (ok[u]) {
+                const int n_own = side ? n2 : n1;
+                j2[u] = side ? idx2[j] : idx1[j];
+                const float *a = (side ? xyz2 : xyz1) + j * 3;
+                ax[u] = a[0]; ay[u] = a[1]; az[u] = a[2];
+                gd[u] = point_grad_coeff(p, side, b, b * n_own + j, side ? v2 : v1);
+            }
         }
-        vec[t * 3 + 0] = gx; vec[t * 3 + 1] = gy; vec[t * 3 + 2] = gz;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int t = base + u * kGradSmemThreads + tid;
+            if (t >= nt) continue;
+            const int side = t >= n1 ? 1 : 0;
+            const int j = side ? t - n1 : t;
+            float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+            if (ok[u]) {
+                const float *o = (side ? xyz1 : xyz2) + j2[u] * 3;
+                const float g = __fmul_rn(gd[u], 2.0f);  // chamfer3D.cu:166
+                gx = __fmul_rn(g, __fsub_rn(ax[u], o[0]));
+                gy = __fmul_rn(g, __fsub_rn(ay[u], o[1]));
+                gz = __fmul_rn(g, __fsub_rn(az[u], o[2]));
+                const int pos = atomicAdd(&seg[(side ? n2 : 0) + j2[u]], 1);
+                lst[(side ? n1 : 0) + pos] = j;
+            }
+            vec[t * 3 + 0] = gx; vec[t * 3 + 1] = gy; vec[t * 3 + 2] = gz;
+        }
     }
     __syncthreads();
     // ---- 4. gather: point j of cloud c sums its own term and, in ascending index order, minus the terms of the points
@@ -1210,9 +1274,9 @@ int launch_nn_variant(int variant, bool exact, const NNParams &p, int B, cudaStr
     switch (variant) {
         case 0: return launch_nn<true, 4, 128, 5>(p, B, st);
         case 1: return launch_nn<true, 4, 128, 6>(p, B, st);
-        case 2: return launch_nn<true, 8, 128, 3>(p, B, st);
-        case 3: return launch_nn<true, 8, 64, 6>(p, B, st);
-        case 4: return launch_nn<true, 16, 64, 4>(p, B, st);
+        case 2: return launch_nn<true, 8, 128, 4>(p, B, st);
+        case 3: return launch_nn<true, 8, 64, 8>(p, B, st);
+        case 4: return launch_nn<true, 6, 128, 4>(p, B, st);
         case 5: return launch_nn<true, 2, 128, 6>(p, B, st);
         case 6: return launch_nn<true, 8, 128, 2>(p, B, st);
         case 7: return launch_nn<true, 4, 64, 8>(p, B, st);
@@ -1371,18 +1435,25 @@ int ured_dcd_forward_ex(const float *dist1, const float *dist2, const int *idx1,
     if (n1 == 0 || n2 == 0) return fail_arg(URED_E_SHAPE, "ured_dcd_forward: empty cloud");
     if (!dist1 || !dist2 || !idx1 || !idx2) return fail_arg(URED_E_NULL, "ured_dcd_forward: NULL input");
     const bool want_loss = loss || ew1 || ew2;
-    const size_t smem = want_loss ? (size_t)(n1 + n2) * sizeof(int) : 0;  // cd_p / cd_t / fscore alone need no histogram
+    const size_t staged_bytes = (size_t)(n1 + n2) * 8;   // histograms / distances (4 B) + terms (4 B) per point
+    const bool staged = staged_bytes <= 200 * 1024;
+    const size_t smem = staged ? staged_bytes : (want_loss ? (size_t)(n1 + n2) * sizeof(int) : 0);  // unstaged: cd_p / cd_t / fscore alone need no histogram
     if (smem > 200 * 1024) return fail_arg(URED_E_RANGE, "ured_dcd_forward: n1 + n2 > 51200 points per pair not supported");
     // (per device, not per thread or process: set before every launch that needs it -- the call is cheap and legal during capture)
     if (smem > 48 * 1024)
-        URED_CUDA(cudaFuncSetAttribute(dcd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "dcd smem attribute");
+        URED_CUDA(staged ? cudaFuncSetAttribute(dcd_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                         : cudaFuncSetAttribute(dcd_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "dcd smem attribute");
     DcdLens lens;
     lens.len1 = len1; lens.len2 = len2; lens.rep1 = rep1; lens.mod2 = mod2; lens.non_reg = (flags & URED_FLAG_NON_REG) ? 1 : 0;
     DcdOut out;
     out.loss = loss; out.cd_p = cd_p; out.cd_t = cd_t; out.ew1 = ew1; out.ew2 = ew2;
     out.fscore = fscore; out.f_threshold = f_threshold; out.B = B;
-    dcd_fwd_kernel<<<B, kDcdThreads, smem, (cudaStream_t)stream>>>(dist1, dist2, idx1, idx2, n1, n2, alpha, n_lambda, frac_12,
-                                                                   frac_21, out, lens);
+    if (staged)
+        dcd_fwd_kernel<true><<<B, kDcdThreads, smem, (cudaStream_t)stream>>>(dist1, dist2, idx1, idx2, n1, n2, alpha, n_lambda, frac_12,
+                                                                             frac_21, out, lens);
+    else
+        dcd_fwd_kernel<false><<<B, kDcdThreads, smem, (cudaStream_t)stream>>>(dist1, dist2, idx1, idx2, n1, n2, alpha, n_lambda, frac_12,
+                                                                              frac_21, out, lens);
     URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "dcd_fwd_kernel launch");
 }

@@ -66,7 +66,25 @@ class GraphedDCD:
         with torch.cuda.graph(self.graph):
             self.loss, self.cd_p, self.cd_t, self.gx, self.ggt = step()
 
-    def __call__(self, x, gt):
+    def _check(self, x, gt):
         if tuple(x.shape) != self.shape_x or tuple(gt.shape) != self.shape_gt:
             raise ValueError(f"GraphedDCD was captured for x {self.shape_x} and gt {self.shape_gt}")
+
+    def __call__(self, x, gt):
+        self._check(x, gt)
         return _Replay.apply(x.float(), gt.float(), self)
+
+    def forward_backward(self, x, gt):
+        """The whole loss step as ONE replay, outside autograd: returns (loss [B], cd_p, cd_t, d sum(loss)/dx, d sum(loss)/dgt).
+
+        For training loops whose objective ends in the DCD loss: feed the gradients on with ``x.backward(gx * scale)``.
+        Two input copies and one graph launch per step -- nothing else touches the GPU -- so a step as small as U-RED's
+        training batch (32 pairs x 2048 points, 0.08 ms of kernels) is no longer bound by the ~15 small torch launches
+        that autograd adds around it.  The returned tensors are the graph's static buffers: valid until the next call.
+        """
+        self._check(x, gt)
+        with torch.no_grad():
+            self.static_x.copy_(x, non_blocking=True)
+            self.static_gt.copy_(gt, non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.cd_p, self.cd_t, self.gx, self.ggt

@@ -481,7 +481,12 @@ def dcd_workload(ctx, wl, steps, warmup, exact_only, peaks, ffma_peak, sampler=N
 
         ms_g, _ = ctx.timed(step_graph, steps, warmup)
         rec["graph"] = {"ms_per_step": ms_g, "value": ctx.world * pairs_per_step / (ms_g * 1e-3) / 1e9,
-                        "what": "GraphedDCD: pack -> nn_kernel -> dcd_fwd_kernel -> grad kernel replayed as one CUDA graph, gradients scaled by the upstream g_loss"}
+                        "what": "GraphedDCD as an autograd op: pack -> nn_kernel -> dcd_fwd_kernel -> grad kernel replayed as one CUDA graph, "
+                                "gradients scaled by the upstream g_loss (torch's own small launches around it remain)"}
+        ms_r, _ = ctx.timed(lambda: g.forward_backward(x_dev, gt_dev), steps, warmup)
+        rec["graph_step"] = {"ms_per_step": ms_r, "value": ctx.world * pairs_per_step / (ms_r * 1e-3) / 1e9,
+                             "what": "GraphedDCD.forward_backward: the whole step (two input copies + one replay of pack, nn_kernel, dcd_fwd_kernel, "
+                                     "grad kernel) outside autograd; returns loss and d sum(loss)/d clouds"}
 
     if with_e2e:
         # ---- end to end: host buffers in, host result out, every step ---------------------------------

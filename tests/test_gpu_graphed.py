@@ -45,3 +45,18 @@ def test_graphed_dcd_matches_eager(ured):
         a, b = x0.detach().requires_grad_(), gt0.detach().requires_grad_()
         dcd(a, b)[0].sum().backward()
     print(f"\ncfg1 step: eager {bench(eager):.3f} ms, graphed {bench(graphed):.3f} ms")
+
+
+def test_graphed_whole_step_replay(ured):
+    """GraphedDCD.forward_backward: loss and d sum(loss)/d clouds of one replay == the eager autograd step, bit for bit
+    (the backward kernel is deterministic), and stays correct when inputs change between replays."""
+    B, N = 16, 2048
+    dcd = ured.GraphedDCD(B, N, N, alpha=200, n_lambda=0.5)
+    for seed in (300, 304, 300):
+        x0, gt0 = make_clouds(seed, B, N, "S").cuda(), (make_clouds(seed + 1, B, N, "S") * 0.9).cuda()
+        loss, cd_p, cd_t, gx, ggt = dcd.forward_backward(x0, gt0)
+        xe, gte = x0.clone().requires_grad_(), gt0.clone().requires_grad_()
+        el, ep, et = ured.calc_dcd(xe, gte, alpha=200, n_lambda=0.5)
+        el.sum().backward()
+        assert torch.equal(loss, el) and torch.equal(cd_p, ep) and torch.equal(cd_t, et)
+        assert torch.equal(gx, xe.grad) and torch.equal(ggt, gte.grad)
