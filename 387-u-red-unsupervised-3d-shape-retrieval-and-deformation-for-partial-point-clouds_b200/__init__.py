@@ -11,7 +11,7 @@ kernels behind include/ured_chamfer.h; there is no CPU, PyTorch or Triton fallba
 """
 from . import _native
 from ._native import NativeLibraryError, build_native
-from .dist_chamfer_3D import chamfer_3DDist, chamfer_3DFunction, nn_forward, nn_backward
+from .dist_chamfer_3D import chamfer_3DDist, chamfer_3DFunction, nn_forward, nn_backward, check_finite
 from .dist_chamfer_3D import chamfer_3DDist as cd
 from .model_utils import calc_cd, calc_dcd, chamfer_ragged, fscore, fscore_fused, torch_epilogue
 from .chamfer_loss import ChamferLoss, chamfer_distance2, compute_cm_loss
@@ -24,7 +24,7 @@ from .retrieval import (RetrievalEngine, PackedClouds, score_all_pairs, write_pa
 from .exchange import PeerExchange
 
 __all__ = [
-    "chamfer_3DDist", "chamfer_3DFunction", "nn_forward", "nn_backward", "cd", "fscore", "calc_cd", "calc_dcd", "chamfer_ragged",
+    "chamfer_3DDist", "chamfer_3DFunction", "nn_forward", "nn_backward", "check_finite", "cd", "fscore", "calc_cd", "calc_dcd", "chamfer_ragged",
     "ChamferLoss", "chamfer_distance2", "compute_cm_loss",
     "knn1_points", "residual_retrieval_loss", "PackedClouds", "RetrievalEngine", "GraphedDCD", "score_candidates", "score_library", "score_all_pairs", "write_pair_pickles", "topk_smallest", "retrieve",
     "retrieve_sharded", "shard_bounds", "merge_topk", "gather_and_merge", "PeerExchange", "fscore_fused", "torch_epilogue",

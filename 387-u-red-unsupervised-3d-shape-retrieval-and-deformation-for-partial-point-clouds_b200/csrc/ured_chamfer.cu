@@ -785,8 +785,8 @@ __device__ __forceinline__ float point_grad_coeff(const GradParams &p, int side,
 template <int PHASE, bool SHARED1, bool SHARED2>
 __global__ void __launch_bounds__(kGradThreads) grad_kernel(const GradParams p) {
     const int per_pair = p.n[0] + p.n[1];
-    const size_t b = blockIdx.y;
-    for (int t = blockIdx.x * kGradThreads + threadIdx.x; t < per_pair; t += gridDim.x * kGradThreads) {
+    const size_t b = blockIdx.x;   // pairs on the x dimension of the grid (2^31 - 1 of them), point slabs on y
+    for (int t = blockIdx.y * kGradThreads + threadIdx.x; t < per_pair; t += gridDim.y * kGradThreads) {
         const int side = t >= p.n[0] ? 1 : 0;
         const int j = side ? t - p.n[0] : t;
         const int n_own = side ? p.n[1] : p.n[0], n_oth = side ? p.n[0] : p.n[1];
@@ -1508,8 +1508,7 @@ int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n
     }
     int gx = (n1 + n2 + kGradThreads - 1) / kGradThreads;
     if (gx > 64) gx = 64;
-    if (B > 65535) return fail_arg(URED_E_SHAPE, "ured_dcd_backward: B > 65535 pairs per call");
-    dim3 grid(gx, B);
+    dim3 grid(B, gx);
     if (!shared1 && !shared2) grad_kernel<0, false, false><<<grid, kGradThreads, 0, st>>>(p);
     else if (shared1 && !shared2) grad_kernel<0, true, false><<<grid, kGradThreads, 0, st>>>(p);
     else if (!shared1 && shared2) grad_kernel<0, false, true><<<grid, kGradThreads, 0, st>>>(p);

@@ -30,6 +30,20 @@ def _require_cloud(name, t):
         raise TypeError(f"{name} must be float32, got {t.dtype}")
 
 
+def check_finite(*clouds):
+    """Raise ValueError if any cloud holds a NaN or an infinity (one reduction + a host sync per cloud).
+
+    Bit-exact parity with the reference is defined for finite coordinates.  On non-finite input this package stays
+    memory-safe (indices in range) but its output is unspecified -- and so, in effect, is the reference's: its kernel
+    admits a NaN distance only as the first candidate of each 512-candidate tile (chamfer3D.cu:36,126), so a NaN point
+    at index 512*t silently removes that whole tile from the search, any other NaN point is merely skipped, and a NaN at
+    index 0 makes every result (NaN, 0).  Set URED_CHECK_FINITE=1 to run this check on every forward call.
+    """
+    for c in clouds:
+        if not bool(torch.isfinite(c).all()):
+            raise ValueError("non-finite coordinate in a point cloud (URED_CHECK_FINITE=1): Chamfer parity is defined for finite inputs only")
+
+
 def _stream(device):
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -59,6 +73,8 @@ def nn_forward(xyz1, xyz2, exact_only=None, len1=None, len2=None):
     m = xyz2.shape[1]
     if xyz2.shape[0] != B:
         raise ValueError(f"batch mismatch: {B} vs {xyz2.shape[0]}")
+    if os.environ.get("URED_CHECK_FINITE", "0") == "1":
+        check_finite(xyz1, xyz2)
     dev = xyz1.device
     dist1 = torch.empty(B, n, device=dev, dtype=torch.float32)
     dist2 = torch.empty(B, m, device=dev, dtype=torch.float32)

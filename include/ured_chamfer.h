@@ -89,7 +89,10 @@ int ured_pack_clouds(const float *xyz, int count, int n, const int *len, void *p
 /* ---- nearest neighbours on packed clouds (both directions, one launch) --------------------
  * dist1/idx1: [B, n1]  for every point of cloud 1, squared distance to / index of its nearest
  *                      point in cloud 2 (lowest index on ties);  dist2/idx2: [B, n2] vice versa.
- * Results are bit-identical to NmDistanceKernel (chamfer3D.cu:12-134) for finite inputs.
+ * Results are bit-identical to NmDistanceKernel (chamfer3D.cu:12-134) for finite inputs.  Non-finite coordinates:
+ * memory-safe (indices stay in range) but unspecified -- the reference admits a NaN distance only as the first
+ * candidate of each of its 512-candidate tiles (chamfer3D.cu:36,126), an artefact this library does not reproduce;
+ * the Python layer offers an opt-in check that raises instead (URED_CHECK_FINITE=1).
  *
  * For shapes whose grid would be too small (few pairs, or very large clouds) the candidate range is split over
  * several CTAs and merged afterwards; that needs `scratch`: ured_nn_scratch_bytes(B, n1, n2) bytes (0 for most

@@ -355,15 +355,18 @@ def test_compute_cm_loss_has_no_per_sample_launches(ured):
             full, part = ured.compute_cm_loss(src, tgt, parts, mask)
             (full + part).backward()
             torch.cuda.synchronize()
-        device_ops = sum(1 for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA)
+        import collections
+        device_ops = collections.Counter(e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA)
         return lib.ured_kernel_launches() - n0, device_ops
 
     run(2, 2)                                   # warm-up (lazy module loads)
+    run(8, 4)
     own_a, all_a = run(2, 2)
     own_b, all_b = run(8, 4)
     assert own_a == own_b
-    assert all_a > 0, "the profiler saw no device activity"
-    assert all_a == all_b, f"device operations grow with the batch: {all_a} for B=2,P=2 vs {all_b} for B=8,P=4"
+    assert sum(all_a.values()) > 0, "the profiler saw no device activity"
+    diff = {k: (all_a.get(k, 0), all_b.get(k, 0)) for k in set(all_a) | set(all_b) if all_a.get(k, 0) != all_b.get(k, 0)}
+    assert sum(all_a.values()) == sum(all_b.values()), f"device operations grow with the batch (B=2,P=2 vs B=8,P=4): {diff}"
 
 
 def test_backward_is_bit_reproducible_and_handles_crowded_points(ured, oracle):
@@ -566,3 +569,54 @@ def test_compat_pytorch3d_subset(ured, oracle):
     assert np.array_equal(knn.idx[..., 0].cpu().numpy(), i1.astype(np.int64))
     with pytest.raises(NotImplementedError):
         ured.compat.knn_points(dev(x0), dev(y0), K=3)
+
+
+def test_non_finite_inputs_policy(ured, oracle, monkeypatch):
+    """Parity is defined for finite clouds.  With a NaN / inf coordinate the call must stay memory-safe (indices in range, other
+    pairs of the batch untouched), and URED_CHECK_FINITE=1 turns it into an error."""
+    a, b = make_clouds(190, 3, 700, "S"), make_clouds(191, 3, 900, "S")
+    bad_a, bad_b = a.clone(), b.clone()
+    bad_a[1, 5, 0] = float("nan")
+    bad_b[1, 512, 2] = float("inf")
+    for exact_only in (False, True):
+        d1, d2, i1, i2 = ured.nn_forward(dev(bad_a), dev(bad_b), exact_only=exact_only)
+        assert int(i1.min()) >= 0 and int(i1.max()) < 900 and int(i2.min()) >= 0 and int(i2.max()) < 700
+        o = oracle.c.chamfer_forward(a.numpy(), b.numpy())
+        for s in (0, 2):                                            # the clean pairs of the batch keep their exact results
+            assert np.array_equal(i1[s].cpu().numpy(), o[2][s]) and np.array_equal(d1[s].cpu().numpy(), o[0][s])
+            assert np.array_equal(i2[s].cpu().numpy(), o[3][s]) and np.array_equal(d2[s].cpu().numpy(), o[1][s])
+    monkeypatch.setenv("URED_CHECK_FINITE", "1")
+    with pytest.raises(ValueError, match="non-finite"):
+        ured.nn_forward(dev(bad_a), dev(bad_b))
+    ured.nn_forward(dev(a), dev(b))                                 # finite clouds pass the check
+
+
+def test_size_limits_at_the_boundary(ured, oracle):
+    """dcd_fwd holds one pair's histograms in shared memory: exactly 51 200 points per pair work, one more is URED_E_RANGE;
+    the general backward takes more than 65 535 pairs per call (it used to put the pairs on gridDim.y)."""
+    lib = ured._native.load()
+    n1, n2 = 25600, 25600
+    x, gt = make_clouds(195, 1, n2, "S"), make_clouds(196, 1, n1, "S")
+    res = ured.calc_dcd(dev(x), dev(gt), alpha=50, n_lambda=1)
+    ref = oracle.t.calc_dcd_oracle(x, gt, alpha=50, n_lambda=1)
+    for got, want in zip(res, ref):
+        assert np.allclose(got.cpu().numpy(), want.numpy(), rtol=RTOL, atol=0)
+    with pytest.raises(ured.NativeLibraryError, match="51200"):
+        ured.calc_dcd(dev(make_clouds(197, 1, n2 + 1, "S")), dev(gt))
+    # 70 000 tiny pairs, one target broadcast over all of them -> general backward kernels (cloud 1 is shared)
+    B = 70000
+    tgt, cands = dev(make_clouds(198, 1, 8, "S")), dev(make_clouds(199, B, 8, "S"))
+    d1, d2, i1, i2 = ured.retrieval.nn_pairs(tgt, cands, B, B, B)
+    g1, g2 = torch.empty(1, 8, 3, device="cuda"), torch.empty(B, 8, 3, device="cuda")
+    w1, w2 = torch.ones(B, 8, device="cuda"), torch.ones(B, 8, device="cuda")
+    rc = lib.ured_chamfer_backward(tgt.data_ptr(), cands.data_ptr(), B, 8, 8, B, B, None, None, w1.data_ptr(), w2.data_ptr(),
+                                   i1.data_ptr(), i2.data_ptr(), g1.data_ptr(), g2.data_ptr(), None)
+    ured._native.check(rc, "ured_chamfer_backward")
+    torch.cuda.synchronize()
+    t64, c64 = tgt.double(), cands.double()
+    diff2 = 2 * (c64 - t64[0][i2.long()])                                    # d dist2 / d candidate point
+    assert torch.allclose(g2.double(), diff2, rtol=1e-5, atol=1e-6)
+    want1 = torch.zeros(8, 3, dtype=torch.float64, device="cuda")
+    want1 += (2 * (t64[0].unsqueeze(0) - torch.gather(c64, 1, i1.long().unsqueeze(-1).expand(-1, -1, 3)))).sum(0)
+    want1.index_add_(0, i2.long().view(-1), (-diff2).view(-1, 3))
+    assert torch.allclose(g1[0].double(), want1, rtol=1e-4, atol=1e-4)
