@@ -61,6 +61,10 @@ int check_cuda(cudaError_t e, const char *where) {
         if (rc_) return rc_;                         \
     } while (0)
 
+// dynamic shared memory above this needs the opt-in attribute: the 48 KB default limit covers static + dynamic shared
+// memory together, and the kernels here declare up to ~1 KB statically
+constexpr size_t kSmemOptIn = 40 * 1024;
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int pad32(int n) { return (n + 31) / 32 * 32; }
 
@@ -199,7 +203,7 @@ __device__ __forceinline__ float exact_d(float cx, float cy, float cz, float qx,
 // Launch variants: T threads per CTA, R queries per thread in registers, MINB resident CTAs per SM (register cap).
 // Few fat warps win on this loop: the FFMA2 stream needs no latency hiding beyond its own ILP, a larger R divides the
 // LDS and chunk-bookkeeping instructions per pair, and a looser register cap lets ptxas keep the half-major order.
-template <bool SCREEN, int R, int T, int MINB>
+template <bool SCREEN, int R, int T, int MINB, bool PF = false>
 __global__ void __launch_bounds__(T, MINB) nn_kernel(const NNParams p) {
     constexpr int NARR = SCREEN ? 4 : 3;
     constexpr int G = kChunk;
@@ -296,17 +300,32 @@ __global__ void __launch_bounds__(T, MINB) nn_kernel(const NNParams p) {
         const float *Z = stage_mem + (s * NARR + 2) * kTile;
         const float *W = stage_mem + (s * NARR + (SCREEN ? 3 : 2)) * kTile;
 
+        // PF: the next group of four candidates is loaded (shared -> registers) while the current one is evaluated, across
+        // chunk boundaries too -- for launches that leave an SM with one or two CTAs, where no other warp hides the LDS latency
+        float4 px = make_float4(0.f, 0.f, 0.f, 0.f), py = px, pz = px, pw = px;
+        if (PF) {
+            px = *reinterpret_cast<const float4 *>(X); py = *reinterpret_cast<const float4 *>(Y);
+            pz = *reinterpret_cast<const float4 *>(Z); pw = *reinterpret_cast<const float4 *>(W);
+        }
         for (int c0 = 0; c0 < tk; c0 += G) {
             float cm[R];
 #pragma unroll
             for (int r = 0; r < R; r++) cm[r] = kInf;
 #pragma unroll
             for (int k = 0; k < G; k += 4) {
-                const float4 x4 = *reinterpret_cast<const float4 *>(X + c0 + k);
-                const float4 y4 = *reinterpret_cast<const float4 *>(Y + c0 + k);
-                const float4 z4 = *reinterpret_cast<const float4 *>(Z + c0 + k);
-                float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (SCREEN) w4 = *reinterpret_cast<const float4 *>(W + c0 + k);
+                float4 x4, y4, z4, w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (PF) {
+                    x4 = px; y4 = py; z4 = pz; w4 = pw;
+                    int nk = c0 + k + 4;
+                    nk = nk < tk ? nk : 0;   // (past the tile: a harmless re-read of its first group)
+                    px = *reinterpret_cast<const float4 *>(X + nk); py = *reinterpret_cast<const float4 *>(Y + nk);
+                    pz = *reinterpret_cast<const float4 *>(Z + nk); pw = *reinterpret_cast<const float4 *>(W + nk);
+                } else {
+                    x4 = *reinterpret_cast<const float4 *>(X + c0 + k);
+                    y4 = *reinterpret_cast<const float4 *>(Y + c0 + k);
+                    z4 = *reinterpret_cast<const float4 *>(Z + c0 + k);
+                    if (SCREEN) w4 = *reinterpret_cast<const float4 *>(W + c0 + k);
+                }
                 // half-major order: one candidate pair against all R queries, layer by layer, so that the 64-bit
                 // candidate operand stays in the operand-reuse slot and only q (1 word) + t (2 words) are read per FFMA2
 #pragma unroll
@@ -530,7 +549,7 @@ const NNVariant kVariants[kNumVariants] = {
     {8, 64, 8},    // 3
     {6, 128, 4},   // 4
     {2, 128, 6},   // 5: smallest tile (256 queries) for launches that cannot fill the machine otherwise
-    {8, 128, 2},   // 6
+    {4, 128, 4},   // 6: with register prefetch of the next candidate group
     {4, 64, 8},    // 7
 };
 constexpr int kDefaultVariant = 0, kSmallVariant = 5;
@@ -1257,13 +1276,13 @@ inline int count2_of(int B, int mod2) { return B < mod2 ? B : mod2; }
 
 inline bool flags_env_general() { return env_int("URED_GRAD_GENERAL", 0) != 0; }  // tests: force the global-atomic backward
 
-template <bool SCREEN, int R, int T, int MINB>
+template <bool SCREEN, int R, int T, int MINB, bool PF = false>
 int launch_nn(const NNParams &p, int B, cudaStream_t st) {
     constexpr int NARR = SCREEN ? 4 : 3;
     const size_t smem = (size_t)kStages * NARR * kTile * sizeof(float);
     const long long grid = (long long)B * (p.qtiles[0] + p.qtiles[1]) * p.nsplit;
     if (grid > 0x7fffffffll) return fail_arg(URED_E_SHAPE, "too many work items for one launch");
-    nn_kernel<SCREEN, R, T, MINB><<<(unsigned)grid, T, smem, st>>>(p);
+    nn_kernel<SCREEN, R, T, MINB, PF><<<(unsigned)grid, T, smem, st>>>(p);
     URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "nn_kernel launch");
 }
@@ -1278,7 +1297,7 @@ int launch_nn_variant(int variant, bool exact, const NNParams &p, int B, cudaStr
         case 3: return launch_nn<true, 8, 64, 8>(p, B, st);
         case 4: return launch_nn<true, 6, 128, 4>(p, B, st);
         case 5: return launch_nn<true, 2, 128, 6>(p, B, st);
-        case 6: return launch_nn<true, 8, 128, 2>(p, B, st);
+        case 6: return launch_nn<true, 4, 128, 4, true>(p, B, st);
         case 7: return launch_nn<true, 4, 64, 8>(p, B, st);
     }
     return fail_arg(URED_E_RANGE, "unknown nn_kernel variant");
@@ -1440,7 +1459,7 @@ int ured_dcd_forward_ex(const float *dist1, const float *dist2, const int *idx1,
     const size_t smem = staged ? staged_bytes : (want_loss ? (size_t)(n1 + n2) * sizeof(int) : 0);  // unstaged: cd_p / cd_t / fscore alone need no histogram
     if (smem > 200 * 1024) return fail_arg(URED_E_RANGE, "ured_dcd_forward: n1 + n2 > 51200 points per pair not supported");
     // (per device, not per thread or process: set before every launch that needs it -- the call is cheap and legal during capture)
-    if (smem > 48 * 1024)
+    if (smem > kSmemOptIn)
         URED_CUDA(staged ? cudaFuncSetAttribute(dcd_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
                          : cudaFuncSetAttribute(dcd_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "dcd smem attribute");
     DcdLens lens;
@@ -1500,7 +1519,7 @@ int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n
     p.one_dir = idx2 ? 0 : 1;   // (ured_nn_backward_one_direction passes no idx2)
     const size_t smem_need = (size_t)(n1 + n2) * 20;  // own terms (12 B) + segment ends (4 B) + lists (4 B) per point
     if (!shared1 && !shared2 && smem_need <= 200 * 1024 && !(flags_env_general())) {
-        if (smem_need > 48 * 1024)
+        if (smem_need > kSmemOptIn)
             URED_CUDA(cudaFuncSetAttribute(grad_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "grad smem attribute");
         grad_gather_kernel<<<B, kGradSmemThreads, smem_need, st>>>(p);
         URED_COUNT_LAUNCH();

@@ -90,18 +90,26 @@ def nn_pairs(cloud1, cloud2, B, rep1, mod2, exact_only=False):
     return dist1, dist2, idx1, idx2
 
 
-def pair_scores(dist1, dist2, idx1, idx2, alpha=1000, n_lambda=1, exact_ranking=False):
+_METRICS = ("dcd", "cd_p", "cd_t")
+
+
+def pair_scores(dist1, dist2, idx1, idx2, alpha=1000, n_lambda=1, exact_ranking=False, metrics=None):
     """(dcd, cd_p, cd_t), each [B], from raw NN results of chamfer(gt, x) (model_utils.py:31-58).
 
     Default: the fused epilogue kernel, whose row means follow torch's reduction order (include/ured_chamfer.h,
     "Reduction order") -- bit-identical to the reference's torch ops for the cloud sizes U-RED uses.
     ``exact_ranking=True`` runs the reference's torch ops themselves on the bit-exact dist/idx (model_utils.py:26-45,
     57-58: exp, scatter_add_, gather, pow, mean): ~25 small launches per call, for audits and for shapes outside the
-    fused kernel's guaranteed range."""
+    fused kernel's guaranteed range.
+
+    ``metrics`` (subset of "dcd", "cd_p", "cd_t"; default all): scores not asked for come back as None -- ranking by
+    cd_t alone skips the histograms and the exp/weight terms of the DCD loss."""
+    metrics = _METRICS if metrics is None else tuple(metrics)
     if exact_ranking:
         from .model_utils import torch_epilogue
         n1, n2 = dist1.shape[1], dist2.shape[1]
-        return torch_epilogue(dist1, dist2, idx1, idx2, alpha, n_lambda, frac_12=n2 / n1, frac_21=n1 / n2)
+        full = torch_epilogue(dist1, dist2, idx1, idx2, alpha, n_lambda, frac_12=n2 / n1, frac_21=n1 / n2)
+        return tuple(v if m in metrics else None for m, v in zip(_METRICS, full))
     lib = _native.load()
     B, n1 = dist1.shape
     n2 = dist2.shape[1]
@@ -111,10 +119,10 @@ def pair_scores(dist1, dist2, idx1, idx2, alpha=1000, n_lambda=1, exact_ranking=
         rc = lib.ured_dcd_forward(_native.ptr(dist1), _native.ptr(dist2), _native.ptr(idx1), _native.ptr(idx2),
                                   B, n1, n2, 1, max(B, 1), None, None,
                                   float(alpha), float(n_lambda), float(n2 / n1), float(n1 / n2), 0,
-                                  _native.ptr(out[0]), _native.ptr(out[1]), _native.ptr(out[2]),
+                                  *[_native.ptr(out[i]) if m in metrics else None for i, m in enumerate(_METRICS)],
                                   None, None, _stream(dev))
     _native.check(rc, "ured_dcd_forward")
-    return out[0], out[1], out[2]
+    return tuple(out[i] if m in metrics else None for i, m in enumerate(_METRICS))
 
 
 def score_candidates(targets, candidates, alpha=1000, n_lambda=1, exact_only=False, exact_ranking=False):
@@ -134,39 +142,42 @@ def score_candidates(targets, candidates, alpha=1000, n_lambda=1, exact_only=Fal
     return {"dcd": dcd.view(Q, K), "cd_p": cd_p.view(Q, K), "cd_t": cd_t.view(Q, K)}
 
 
-def score_library(targets, library, alpha=1000, n_lambda=1, max_pairs=8192, exact_only=False, exact_ranking=False):
-    """Score every target [Q, N, 3] against every library shape: {"dcd","cd_p","cd_t"} each [Q, S].
+def score_library(targets, library, alpha=1000, n_lambda=1, max_pairs=8192, exact_only=False, exact_ranking=False, metrics=None):
+    """Score every target [Q, N, 3] against every library shape: {"dcd","cd_p","cd_t"} each [Q, S] (or the subset ``metrics``).
 
     ``library`` is a PackedClouds (packed once, kept resident) or a [S, M, 3] tensor.  Work is cut
     into slabs of at most ``max_pairs`` (target, shape) pairs so that the per-point NN results
     (8 bytes per point per pair) stay a bounded scratch buffer instead of Q*S*(N+M)*8 bytes.
     """
+    metrics = _METRICS if metrics is None else tuple(metrics)
     tgts = _as_packed(targets.float() if not isinstance(targets, PackedClouds) else targets)
     lib_c = _as_packed(library)
     Q, S = tgts.count, lib_c.count
-    out = torch.empty(3, Q, S, device=tgts.device, dtype=torch.float32)
+    out = torch.empty(len(metrics), Q, S, device=tgts.device, dtype=torch.float32)
+    result = {m: out[i] for i, m in enumerate(metrics)}
     if S == 0 or Q == 0:
-        return {"dcd": out[0], "cd_p": out[1], "cd_t": out[2]}
+        return result
+    kw = dict(alpha=alpha, n_lambda=n_lambda, exact_ranking=exact_ranking, metrics=metrics)
     q_step = max(1, min(Q, max_pairs // S)) if S <= max_pairs else 1
     for q0 in range(0, Q, q_step):
         q1 = min(Q, q0 + q_step)
         sub_t = tgts.slice(q0, q1)
         if S <= max_pairs:
             raw = nn_pairs(sub_t, lib_c, (q1 - q0) * S, S, S, exact_only=exact_only)
-            dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda, exact_ranking=exact_ranking)
-            out[0, q0:q1] = dcd.view(q1 - q0, S)
-            out[1, q0:q1] = cd_p.view(q1 - q0, S)
-            out[2, q0:q1] = cd_t.view(q1 - q0, S)
+            sc = dict(zip(_METRICS, pair_scores(*raw, **kw)))
+            if q_step == Q:                      # one slab covers everything: hand the kernel's output back without a copy
+                return {m: sc[m].view(Q, S) for m in metrics}
+            for m in metrics:
+                result[m][q0:q1] = sc[m].view(q1 - q0, S)
         else:  # one target at a time against slabs of the library
             for s0 in range(0, S, max_pairs):
                 s1 = min(S, s0 + max_pairs)
                 slab = lib_c.slice(s0, s1)
                 raw = nn_pairs(sub_t, slab, s1 - s0, s1 - s0, s1 - s0, exact_only=exact_only)
-                dcd, cd_p, cd_t = pair_scores(*raw, alpha=alpha, n_lambda=n_lambda, exact_ranking=exact_ranking)
-                out[0, q0, s0:s1] = dcd
-                out[1, q0, s0:s1] = cd_p
-                out[2, q0, s0:s1] = cd_t
-    return {"dcd": out[0], "cd_p": out[1], "cd_t": out[2]}
+                sc = dict(zip(_METRICS, pair_scores(*raw, **kw)))
+                for m in metrics:
+                    result[m][q0, s0:s1] = sc[m]
+    return result
 
 
 def score_all_pairs(library, alpha=1000, n_lambda=1, max_pairs=8192, exact_only=False):
@@ -232,7 +243,7 @@ def topk_smallest(scores, k, idx_offset=0):
 
 def retrieve(targets, library, k=10, metric="cd_t", **score_kw):
     """Top-k library shapes per target: (scores [Q,k], shape ids int32 [Q,k])."""
-    scores = score_library(targets, library, **score_kw)[metric]
+    scores = score_library(targets, library, metrics=(metric,), **score_kw)[metric]
     return topk_smallest(scores, min(k, scores.shape[1]))
 
 
@@ -297,7 +308,7 @@ def retrieve_sharded(targets, local_library, shard_offset, k=10, metric="cd_t", 
         ls = torch.empty(Q, 0, device=dev, dtype=torch.float32)
         li = torch.empty(Q, 0, device=dev, dtype=torch.int32)
     else:
-        scores = score_library(targets, lib_c, **score_kw)[metric]
+        scores = score_library(targets, lib_c, metrics=(metric,), **score_kw)[metric]
         ls, li = topk_smallest(scores, min(k, lib_c.count), idx_offset=shard_offset)
     return gather_and_merge(ls, li, k, group=group)
 
@@ -349,7 +360,7 @@ class RetrievalEngine:
         if self.lib is None or self.lib.count == 0:
             return torch.empty(self.Q, 0, device=targets.device, dtype=torch.float32)
         return score_library(targets, self.lib, alpha=self.alpha, n_lambda=self.n_lambda, max_pairs=self.max_pairs,
-                             exact_ranking=self.exact_ranking)[self.metric]
+                             exact_ranking=self.exact_ranking, metrics=(self.metric,))[self.metric]
 
     def _pipeline(self, targets):
         Q, k = self.Q, self.k

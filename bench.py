@@ -188,8 +188,11 @@ class Ctx:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
+            # rank 0 prints exactly one JSON line on stdout: NCCL's version banner (NCCL_DEBUG=VERSION and above) must not join it
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-                os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+                os.environ.pop("NCCL_DEBUG", None)
+            else:
+                os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=self.dev)
         self.lib = ured._native.load()
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
