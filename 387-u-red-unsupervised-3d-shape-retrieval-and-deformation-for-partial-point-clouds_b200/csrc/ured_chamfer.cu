@@ -687,31 +687,44 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
         __syncthreads();
     }
     // model_utils.py:31,35-37: exp(-d*alpha); (count**lambda + 1e-6)**(-1) * frac; the term is 1 - e*w
-    auto ew_of = [&](float dk, int c, float frac) {
-        const float e = expf(__fmul_rn(-dk, alpha));
-        const float w = __fmul_rn(__fdiv_rn(1.0f, __fadd_rn(pow_lambda((float)c, n_lambda), 1e-6f)), frac);
-        return __fmul_rn(e, w);
+    auto weight_of = [&](int c, float frac) {
+        return __fmul_rn(__fdiv_rn(1.0f, __fadd_rn(pow_lambda((float)c, n_lambda), 1e-6f)), frac);
     };
     if (STAGED) {
         if (want_loss) {
+            // the weight depends on the BIN only: turn the counts into weights in place (one division per bin instead of one
+            // per point, no data-dependent work left in the per-point loop), then stream the points of each side
+            float *w1 = reinterpret_cast<float *>(count1), *w2 = reinterpret_cast<float *>(count2);
+            for (int j = tid; j < n2_max; j += kDcdThreads) w1[j] = weight_of(count1[j], frac_21);
+            for (int j = tid; j < n1_max; j += kDcdThreads) w2[j] = weight_of(count2[j], frac_12);
+            __syncthreads();
+            const float neg_alpha = -alpha;
+            float *__restrict__ e1 = out.ew1 ? out.ew1 + b * n1_max : nullptr;
+            float *__restrict__ e2 = out.ew2 ? out.ew2 + b * n2_max : nullptr;
 #pragma unroll 4
-            for (int t = tid; t < nt_max; t += kDcdThreads) {
-                const int side = t >= n1_max ? 1 : 0;
-                const int k = side ? t - n1_max : t;
-                const bool valid = k < (side ? n2 : n1);
-                float ewk = 0.0f;
-                if (valid) ewk = ew_of(side ? d2[k] : d1[k], side ? count2[i2[k]] : count1[i1[k]], side ? frac_12 : frac_21);
-                float *ew = side ? out.ew2 : out.ew1;
-                if (ew) ew[b * (side ? n2_max : n1_max) + k] = ewk;   // (zero past the valid length of a ragged cloud)
-                term[t] = __fsub_rn(1.0f, ewk);
+            for (int k = tid; k < n1; k += kDcdThreads) {
+                const float ewk = __fmul_rn(expf(__fmul_rn(d1[k], neg_alpha)), w1[i1[k]]);   // (-d)*alpha == d*(-alpha) bit for bit
+                if (e1) e1[k] = ewk;
+                term[k] = __fsub_rn(1.0f, ewk);
             }
-            __syncthreads();   // every count has been read: the histogram space now takes the distances
+#pragma unroll 4
+            for (int k = tid; k < n2; k += kDcdThreads) {
+                const float ewk = __fmul_rn(expf(__fmul_rn(d2[k], neg_alpha)), w2[i2[k]]);
+                if (e2) e2[k] = ewk;
+                term[n1_max + k] = __fsub_rn(1.0f, ewk);
+            }
+            if (e1) for (int k = n1 + tid; k < n1_max; k += kDcdThreads) e1[k] = 0.0f;   // past the valid length of a ragged cloud
+            if (e2) for (int k = n2 + tid; k < n2_max; k += kDcdThreads) e2[k] = 0.0f;
+            __syncthreads();   // every weight has been read: the histogram space now takes the distances
         }
         float *sd = reinterpret_cast<float *>(hist);
 #pragma unroll 4
-        for (int t = tid; t < nt_max; t += kDcdThreads) sd[t] = t >= n1_max ? d2[t - n1_max] : d1[t];
+        for (int k = tid; k < n1_max; k += kDcdThreads) sd[k] = d1[k];
+#pragma unroll 4
+        for (int k = tid; k < n2_max; k += kDcdThreads) sd[n1_max + k] = d2[k];
         __syncthreads();
     }
+    auto ew_of = [&](float dk, int c, float frac) { return __fmul_rn(expf(__fmul_rn(-dk, alpha)), weight_of(c, frac)); };
 
     // warps 0-2: side 1 (term, d, sqrt d); warps 3-5: side 2; warps 6, 7: F-score counts of side 1 / 2
     const int side = warp < 6 ? warp / 3 : warp - 6;
@@ -897,6 +910,84 @@ __device__ __forceinline__ void block_exclusive_scan(int *a, int n, int *scratch
     __syncthreads();
 }
 
+// one side of the pair: own terms of its `v_own` valid points -> vec_own, and every point filed under the point it chose
+// (pos = seg_bins[choice]++ leaves seg_bins[bin] = END of the bin's segment).  Loads are issued four points at a time.
+struct GradSide {
+    const float *xyz_own, *xyz_oth;   // this pair's clouds
+    const int *idx;                   // argmin of every own point in the other cloud
+    const float *g_dist, *dist, *ew;  // per-point upstream inputs of this side (any may be NULL), already offset to the pair
+    float k_t, k_p, k_l, alpha;       // per-pair coefficients of cd_t, cd_p and the DCD loss (0 when not requested)
+    int v_own;
+};
+__device__ __forceinline__ void grad_own_terms(const GradSide &sd, float *__restrict__ vec_own, int n_own, int *seg_bins, int *lst_own,
+                                               bool file) {
+    constexpr int U = 4;
+    const int tid = threadIdx.x;
+    for (int base = 0; base < n_own; base += kGradSmemThreads * U) {
+        int j2[U];
+        float gd[U], ax[U], ay[U], az[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = base + u * kGradSmemThreads + tid;
+            j2[u] = -1; gd[u] = 0.0f; ax[u] = ay[u] = az[u] = 0.0f;
+            if (j < sd.v_own) {
+                j2[u] = sd.idx[j];
+                ax[u] = sd.xyz_own[j * 3 + 0]; ay[u] = sd.xyz_own[j * 3 + 1]; az[u] = sd.xyz_own[j * 3 + 2];
+                float g = sd.g_dist ? sd.g_dist[j] : 0.0f;
+                if (sd.k_t != 0.0f) g += sd.k_t;
+                if (sd.dist) g += sd.k_p * (0.5f / sqrtf(sd.dist[j]));
+                if (sd.ew) g += sd.k_l * (sd.alpha * sd.ew[j]);
+                gd[u] = g;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = base + u * kGradSmemThreads + tid;
+            if (j >= n_own) continue;
+            float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+            if (j2[u] >= 0) {
+                const float *o = sd.xyz_oth + j2[u] * 3;
+                const float g = __fmul_rn(gd[u], 2.0f);  // chamfer3D.cu:166
+                gx = __fmul_rn(g, __fsub_rn(ax[u], o[0]));
+                gy = __fmul_rn(g, __fsub_rn(ay[u], o[1]));
+                gz = __fmul_rn(g, __fsub_rn(az[u], o[2]));
+                if (file) lst_own[atomicAdd(&seg_bins[j2[u]], 1)] = j;
+            }
+            vec_own[j * 3 + 0] = gx; vec_own[j * 3 + 1] = gy; vec_own[j * 3 + 2] = gz;
+        }
+    }
+}
+
+// point j of one cloud: its own term minus, in ascending index order, the terms of the other cloud's points that chose it
+__device__ __forceinline__ void grad_gather_side(const float *__restrict__ vec_own, const float *__restrict__ vec_oth, int n_own,
+                                                 const int *seg_bins, int *lst_oth, const int *idx_oth, int v_oth,
+                                                 float *__restrict__ grad_out) {
+    for (int j = threadIdx.x; j < n_own; j += kGradSmemThreads) {
+        const int start = j == 0 ? 0 : seg_bins[j - 1], end = seg_bins[j];
+        float ax = vec_own[j * 3 + 0], ay = vec_own[j * 3 + 1], az = vec_own[j * 3 + 2];
+        if (end - start == 1) {                                  // the common case: chosen by exactly one point
+            const int i = lst_oth[start];
+            ax = __fsub_rn(ax, vec_oth[i * 3 + 0]); ay = __fsub_rn(ay, vec_oth[i * 3 + 1]); az = __fsub_rn(az, vec_oth[i * 3 + 2]);
+        } else if (end - start <= kGradSortMax) {
+            for (int u = start + 1; u < end; u++) {              // insertion sort of a short, thread-private segment
+                const int key = lst_oth[u];
+                int w = u - 1;
+                while (w >= start && lst_oth[w] > key) { lst_oth[w + 1] = lst_oth[w]; w--; }
+                lst_oth[w + 1] = key;
+            }
+            for (int u = start; u < end; u++) {
+                const int i = lst_oth[u];
+                ax = __fsub_rn(ax, vec_oth[i * 3 + 0]); ay = __fsub_rn(ay, vec_oth[i * 3 + 1]); az = __fsub_rn(az, vec_oth[i * 3 + 2]);
+            }
+        } else {
+            for (int i = 0; i < v_oth; i++)                      // ascending scan of the other cloud's argmins
+                if (idx_oth[i] == j) { ax = __fsub_rn(ax, vec_oth[i * 3 + 0]); ay = __fsub_rn(ay, vec_oth[i * 3 + 1]); az = __fsub_rn(az, vec_oth[i * 3 + 2]); }
+        }
+        // straight to global memory (consecutive threads write consecutive 12-byte triples)
+        grad_out[j * 3 + 0] = ax; grad_out[j * 3 + 1] = ay; grad_out[j * 3 + 2] = az;
+    }
+}
+
 __global__ void __launch_bounds__(kGradSmemThreads) grad_gather_kernel(const GradParams p) {
     extern __shared__ float gsm[];
     __shared__ int scan_scratch[33];
@@ -904,106 +995,49 @@ __global__ void __launch_bounds__(kGradSmemThreads) grad_gather_kernel(const Gra
     const int tid = threadIdx.x;
     const int n1 = p.n[0], n2 = p.n[1], nt = n1 + n2;
     float *vec = gsm;                                   // [nt * 3]
-    int *seg = reinterpret_cast<int *>(gsm + nt * 3);   // [n2 | n1]: bins of side-1 lists (points of cloud 2), then of side-2 lists
-    int *lst = seg + nt;                                // [n1 | n2]
+    int *seg = reinterpret_cast<int *>(gsm + nt * 3);   // [n2 | n1]: bins over the points of cloud 2 (chosen by cloud 1), then over cloud 1
+    int *lst = seg + nt;                                // [n1 | n2]: cloud-1 points grouped by their choice, then cloud-2 points
     const float *xyz1 = p.xyz[0] + b * n1 * 3, *xyz2 = p.xyz[1] + b * n2 * 3;
-    const int *idx1 = p.idx[0] + b * n1, *idx2 = p.idx[1] + b * n2;
-    const int v1 = valid_len(p.len[0], b, n1), v2 = valid_len(p.len[1], b, n2);
-    const bool live = v1 > 0 && v2 > 0;  // an empty side: no matches, zero gradients
+    const int *idx1 = p.idx[0] + b * n1, *idx2 = p.idx[1] ? p.idx[1] + b * n2 : nullptr;
+    int v1 = valid_len(p.len[0], b, n1), v2 = valid_len(p.len[1], b, n2);
+    if (v1 == 0 || v2 == 0) { v1 = 0; v2 = 0; }          // an empty side: no matches, zero gradients
+    const int q2 = p.one_dir ? 0 : v2;                   // cloud-2 points that searched cloud 1
 
     // ---- 1. histogram of the argmins (bins = the points being chosen) ----------------------------------------------
     for (int k = tid; k < nt; k += kGradSmemThreads) seg[k] = 0;
     __syncthreads();
-    if (live) {
 #pragma unroll 4
-        for (int i = tid; i < v1; i += kGradSmemThreads) atomicAdd(&seg[idx1[i]], 1);          // integer shared atomics are native
-        if (!p.one_dir) {
+    for (int i = tid; i < v1; i += kGradSmemThreads) atomicAdd(&seg[idx1[i]], 1);          // integer shared atomics are native
 #pragma unroll 4
-            for (int i = tid; i < v2; i += kGradSmemThreads) atomicAdd(&seg[n2 + idx2[i]], 1);
-        }
-    }
+    for (int i = tid; i < q2; i += kGradSmemThreads) atomicAdd(&seg[n2 + idx2[i]], 1);
     __syncthreads();
     // ---- 2. segment starts ------------------------------------------------------------------------------------------
     block_exclusive_scan(seg, n2, scan_scratch);
     block_exclusive_scan(seg + n2, n1, scan_scratch);
-    // ---- 3. own terms + grouping: pos = seg[bin]++ leaves seg[bin] = END of the bin's segment ------------------------
-    // Four points per thread and step, in two sweeps: first every independent load (argmin, own coordinates, upstream
-    // coefficient), then the dependent gathers of the chosen points -- the step is bound by memory latency, so what
-    // matters is how many loads are in flight, not how many instructions run.
-    constexpr int U = 4;
-    for (int base = 0; base < nt; base += kGradSmemThreads * U) {
-        int j2[U];
-        float gd[U], ax[U], ay[U], az[U];
-        bool ok[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int t = base + u * kGradSmemThreads + tid;
-            const int side = t >= n1 ? 1 : 0;
-            const int j = side ? t - n1 : t;
-            ok[u] = t < nt && live && j < (side ? v2 : v1) && !(side && p.one_dir);
-            j2[u] = 0; gd[u] = 0.0f; ax[u] = ay[u] = az[u] = 0.0f;
-            if (ok[u]) {
-                const int n_own = side ? n2 : n1;
-                j2[u] = side ? idx2[j] : idx1[j];
-                const float *a = (side ? xyz2 : xyz1) + j * 3;
-                ax[u] = a[0]; ay[u] = a[1]; az[u] = a[2];
-                gd[u] = point_grad_coeff(p, side, b, b * n_own + j, side ? v2 : v1);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int t = base + u * kGradSmemThreads + tid;
-            if (t >= nt) continue;
-            const int side = t >= n1 ? 1 : 0;
-            const int j = side ? t - n1 : t;
-            float gx = 0.0f, gy = 0.0f, gz = 0.0f;
-            if (ok[u]) {
-                const float *o = (side ? xyz1 : xyz2) + j2[u] * 3;
-                const float g = __fmul_rn(gd[u], 2.0f);  // chamfer3D.cu:166
-                gx = __fmul_rn(g, __fsub_rn(ax[u], o[0]));
-                gy = __fmul_rn(g, __fsub_rn(ay[u], o[1]));
-                gz = __fmul_rn(g, __fsub_rn(az[u], o[2]));
-                const int pos = atomicAdd(&seg[(side ? n2 : 0) + j2[u]], 1);
-                lst[(side ? n1 : 0) + pos] = j;
-            }
-            vec[t * 3 + 0] = gx; vec[t * 3 + 1] = gy; vec[t * 3 + 2] = gz;
-        }
-    }
+    // ---- 3. own terms + grouping ------------------------------------------------------------------------------------
+    GradSide s1, s2;
+    s1.xyz_own = xyz1; s1.xyz_oth = xyz2; s1.idx = idx1; s1.v_own = v1;
+    s1.g_dist = p.g_dist[0] ? p.g_dist[0] + b * n1 : nullptr;
+    s1.dist = p.g_cd_p ? p.dist[0] + b * n1 : nullptr;
+    s1.ew = p.g_loss ? p.ew[0] + b * n1 : nullptr;
+    s1.k_t = p.g_cd_t ? p.g_cd_t[b] / (float)max(v1, 1) : 0.0f;
+    s1.k_p = p.g_cd_p ? p.g_cd_p[b] * 0.5f / (float)max(v1, 1) : 0.0f;
+    s1.k_l = p.g_loss ? p.g_loss[b] * 0.5f / (float)max(v1, 1) : 0.0f;
+    s1.alpha = s2.alpha = p.alpha;
+    s2.xyz_own = xyz2; s2.xyz_oth = xyz1; s2.idx = idx2; s2.v_own = q2;
+    s2.g_dist = p.g_dist[1] ? p.g_dist[1] + b * n2 : nullptr;
+    s2.dist = p.g_cd_p ? p.dist[1] + b * n2 : nullptr;
+    s2.ew = p.g_loss ? p.ew[1] + b * n2 : nullptr;
+    s2.k_t = p.g_cd_t ? p.g_cd_t[b] / (float)max(v2, 1) : 0.0f;
+    s2.k_p = p.g_cd_p ? p.g_cd_p[b] * 0.5f / (float)max(v2, 1) : 0.0f;
+    s2.k_l = p.g_loss ? p.g_loss[b] * 0.5f / (float)max(v2, 1) : 0.0f;
+    grad_own_terms(s1, vec, n1, seg, lst, true);
+    grad_own_terms(s2, vec + n1 * 3, n2, seg + n2, lst + n1, true);
     __syncthreads();
-    // ---- 4. gather: point j of cloud c sums its own term and, in ascending index order, minus the terms of the points
-    //         of the other cloud that chose it -------------------------------------------------------------------------
-    for (int t = tid; t < nt; t += kGradSmemThreads) {
-        const int side = t >= n1 ? 1 : 0;          // the cloud this point belongs to
-        const int j = side ? t - n1 : t;
-        // points of the OTHER cloud pointing at j: side-0 points are chosen by cloud-2 points (lists of side 1) and vice versa
-        const int *sg = side ? seg : seg + n2;     // bins over this cloud's points
-        int *ls = side ? lst : lst + n1;           // lists of the other cloud's points
-        const float *ov = side ? vec : vec + n1 * 3;
-        const int start = j == 0 ? 0 : sg[j - 1], end = sg[j];
-        const int len = end - start;
-        float ax = vec[t * 3 + 0], ay = vec[t * 3 + 1], az = vec[t * 3 + 2];
-        if (len <= kGradSortMax) {
-            for (int u = start + 1; u < end; u++) {             // insertion sort of a short, thread-private segment
-                const int key = ls[u];
-                int w = u - 1;
-                while (w >= start && ls[w] > key) { ls[w + 1] = ls[w]; w--; }
-                ls[w + 1] = key;
-            }
-            for (int u = start; u < end; u++) {
-                const int i = ls[u];
-                ax = __fsub_rn(ax, ov[i * 3 + 0]); ay = __fsub_rn(ay, ov[i * 3 + 1]); az = __fsub_rn(az, ov[i * 3 + 2]);
-            }
-        } else {
-            const int *oidx = side ? idx1 : idx2;               // ascending scan of the other cloud's argmins
-            const int n_oth = side ? v1 : v2;
-            for (int i = 0; i < n_oth; i++)
-                if (oidx[i] == j) { ax = __fsub_rn(ax, ov[i * 3 + 0]); ay = __fsub_rn(ay, ov[i * 3 + 1]); az = __fsub_rn(az, ov[i * 3 + 2]); }
-        }
-        // straight to global memory (consecutive threads write consecutive 12-byte triples); vec keeps the own terms,
-        // which other threads are still reading
-        float *dst = (side ? p.grad[1] + b * n2 * 3 : p.grad[0] + b * n1 * 3) + j * 3;
-        dst[0] = ax; dst[1] = ay; dst[2] = az;
-    }
+    // ---- 4. gather ----------------------------------------------------------------------------------------------------
+    // cloud-1 point j was chosen by the cloud-2 points filed in bins seg[n2 + j]; cloud-2 point j by the cloud-1 points in seg[j]
+    grad_gather_side(vec, vec + n1 * 3, n1, seg + n2, lst + n1, idx2, q2, p.grad[0] + b * n1 * 3);
+    grad_gather_side(vec + n1 * 3, vec, n2, seg, lst, idx1, v1, p.grad[1] + b * n2 * 3);
 }
 
 // ------------------------------------------------------------------------------------------

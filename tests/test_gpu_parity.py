@@ -614,9 +614,12 @@ def test_size_limits_at_the_boundary(ured, oracle):
     ured._native.check(rc, "ured_chamfer_backward")
     torch.cuda.synchronize()
     t64, c64 = tgt.double(), cands.double()
-    diff2 = 2 * (c64 - t64[0][i2.long()])                                    # d dist2 / d candidate point
-    assert torch.allclose(g2.double(), diff2, rtol=1e-5, atol=1e-6)
-    want1 = torch.zeros(8, 3, dtype=torch.float64, device="cuda")
-    want1 += (2 * (t64[0].unsqueeze(0) - torch.gather(c64, 1, i1.long().unsqueeze(-1).expand(-1, -1, 3)))).sum(0)
+    diff2 = 2 * (c64 - t64[0][i2.long()])                                    # own terms of the candidate points
+    chosen = torch.gather(c64, 1, i1.long().unsqueeze(-1).expand(-1, -1, 3))  # [B, 8, 3]: the candidate each target point chose
+    diff1 = 2 * (t64[0].unsqueeze(0) - chosen)                               # own terms of the (broadcast) target points, per pair
+    want2 = diff2.clone()
+    want2.scatter_add_(1, i1.long().unsqueeze(-1).expand(-1, -1, 3), -diff1)  # ... scattered onto the chosen candidates
+    assert torch.allclose(g2.double(), want2, rtol=1e-5, atol=1e-6)
+    want1 = diff1.sum(0)
     want1.index_add_(0, i2.long().view(-1), (-diff2).view(-1, 3))
-    assert torch.allclose(g1[0].double(), want1, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(g1[0].double(), want1, rtol=1e-4, atol=1e-3)
