@@ -176,3 +176,21 @@ def test_sharded_engine_two_real_ranks(ured, tmp_path):
     for r in res:
         for mode in ("peer-eager", "peer-graph", "nccl-eager"):
             assert torch.equal(r[mode], want), f"{mode}: sharded ids differ from the one-rank ranking"
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs on the box")
+def test_large_shared_memory_kernels_on_two_devices_from_one_thread(ured):
+    """The > 48 KB shared-memory opt-in is a per-device function attribute: one host thread calling on cuda:0 and then on
+    cuda:1 must work on both (it used to be cached per thread, so the second device failed with cudaErrorInvalidValue)."""
+    from conftest import make_clouds
+    outs = []
+    for d in (0, 1, 0):
+        devd = torch.device("cuda", d)
+        x = make_clouds(400, 2, 4096, "S").to(devd).requires_grad_()       # 4096 + 4096 points: 160 KB in the backward, 64 KB in dcd_fwd
+        gt = make_clouds(401, 2, 4096, "S").to(devd).requires_grad_()
+        loss, cd_p, cd_t = ured.calc_dcd(x, gt, alpha=100, n_lambda=1)
+        loss.sum().backward()
+        torch.cuda.synchronize(devd)
+        outs.append((loss.detach().cpu(), x.grad.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])
