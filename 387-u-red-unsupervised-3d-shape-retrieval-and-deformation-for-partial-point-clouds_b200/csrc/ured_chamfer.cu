@@ -633,6 +633,29 @@ __device__ __forceinline__ float torch_row_sum(F f, int n, int mis, int lane) {
     return v;
 }
 
+// The same sum over a row staged in shared memory, SQRT: of the square roots.  Aligned rows (the usual case) take 128-bit
+// loads and no per-element index arithmetic; the order of the additions is the one above.
+template <bool SQRT>
+__device__ __forceinline__ float torch_row_sum_staged(const float *row, int n, int mis, int lane) {
+    auto f = [&](float v) { return SQRT ? sqrtf(v) : v; };
+    if (mis != 0 || (reinterpret_cast<uintptr_t>(row) & 15u) != 0)
+        return torch_row_sum([&](int k) { return f(row[k]); }, n, mis, lane);
+    float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+    const float4 *row4 = reinterpret_cast<const float4 *>(row);
+    const int nvec = n >> 2;
+#pragma unroll 4
+    for (int idx = lane; idx < nvec; idx += 32) {
+        const float4 v = row4[idx];
+        acc0 = __fadd_rn(acc0, f(v.x)); acc1 = __fadd_rn(acc1, f(v.y)); acc2 = __fadd_rn(acc2, f(v.z)); acc3 = __fadd_rn(acc3, f(v.w));
+    }
+    const int tail = (nvec << 2) + lane;
+    if (tail < n) acc0 = __fadd_rn(acc0, f(row[tail]));
+    float v = __fadd_rn(__fadd_rn(__fadd_rn(acc0, acc1), acc2), acc3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
 struct DcdOut {
     float *loss, *cd_p, *cd_t, *ew1, *ew2;
     float *fscore;      // optional [3, B]: f-score, precision_1, precision_2 (metrics/CD/fscore.py:3-16)
@@ -680,10 +703,24 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
     if (want_loss) {
         for (int k = tid; k < nt_max; k += kDcdThreads) hist[k] = 0;
         __syncthreads();
+        // (rows are 16-byte aligned whenever the row stride is a multiple of four points: 128-bit loads, four points per thread and step)
+        const bool vec1 = (n1_max & 3) == 0 && (reinterpret_cast<uintptr_t>(i1) & 15u) == 0;
+        const bool vec2 = (n2_max & 3) == 0 && (reinterpret_cast<uintptr_t>(i2) & 15u) == 0;
+        auto hist_side = [&](const int *__restrict__ ix, int n, bool vec, int *cnt) {
+            int k0 = 0;
+            if (vec) {
+                const int4 *ix4 = reinterpret_cast<const int4 *>(ix);
 #pragma unroll 4
-        for (int k = tid; k < n1; k += kDcdThreads) atomicAdd(&count1[i1[k]], 1);
-#pragma unroll 4
-        for (int k = tid; k < n2; k += kDcdThreads) atomicAdd(&count2[i2[k]], 1);
+                for (int q = tid; q < (n >> 2); q += kDcdThreads) {
+                    const int4 v = ix4[q];
+                    atomicAdd(&cnt[v.x], 1); atomicAdd(&cnt[v.y], 1); atomicAdd(&cnt[v.z], 1); atomicAdd(&cnt[v.w], 1);
+                }
+                k0 = n & ~3;
+            }
+            for (int k = k0 + tid; k < n; k += kDcdThreads) atomicAdd(&cnt[ix[k]], 1);
+        };
+        hist_side(i1, n1, vec1, count1);
+        hist_side(i2, n2, vec2, count2);
         __syncthreads();
     }
     // model_utils.py:31,35-37: exp(-d*alpha); (count**lambda + 1e-6)**(-1) * frac; the term is 1 - e*w
@@ -691,6 +728,8 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
         return __fmul_rn(__fdiv_rn(1.0f, __fadd_rn(pow_lambda((float)c, n_lambda), 1e-6f)), frac);
     };
     if (STAGED) {
+        const bool vd1 = (n1_max & 3) == 0 && (reinterpret_cast<uintptr_t>(d1) & 15u) == 0 && (reinterpret_cast<uintptr_t>(i1) & 15u) == 0;
+        const bool vd2 = (n2_max & 3) == 0 && (reinterpret_cast<uintptr_t>(d2) & 15u) == 0 && (reinterpret_cast<uintptr_t>(i2) & 15u) == 0;
         if (want_loss) {
             // the weight depends on the BIN only: turn the counts into weights in place (one division per bin instead of one
             // per point, no data-dependent work left in the per-point loop), then stream the points of each side
@@ -698,30 +737,51 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
             for (int j = tid; j < n2_max; j += kDcdThreads) w1[j] = weight_of(count1[j], frac_21);
             for (int j = tid; j < n1_max; j += kDcdThreads) w2[j] = weight_of(count2[j], frac_12);
             __syncthreads();
-            const float neg_alpha = -alpha;
-            float *__restrict__ e1 = out.ew1 ? out.ew1 + b * n1_max : nullptr;
-            float *__restrict__ e2 = out.ew2 ? out.ew2 + b * n2_max : nullptr;
-#pragma unroll 4
-            for (int k = tid; k < n1; k += kDcdThreads) {
-                const float ewk = __fmul_rn(expf(__fmul_rn(d1[k], neg_alpha)), w1[i1[k]]);   // (-d)*alpha == d*(-alpha) bit for bit
-                if (e1) e1[k] = ewk;
-                term[k] = __fsub_rn(1.0f, ewk);
-            }
-#pragma unroll 4
-            for (int k = tid; k < n2; k += kDcdThreads) {
-                const float ewk = __fmul_rn(expf(__fmul_rn(d2[k], neg_alpha)), w2[i2[k]]);
-                if (e2) e2[k] = ewk;
-                term[n1_max + k] = __fsub_rn(1.0f, ewk);
-            }
-            if (e1) for (int k = n1 + tid; k < n1_max; k += kDcdThreads) e1[k] = 0.0f;   // past the valid length of a ragged cloud
-            if (e2) for (int k = n2 + tid; k < n2_max; k += kDcdThreads) e2[k] = 0.0f;
+            const float neg_alpha = -alpha;   // (-d)*alpha == d*(-alpha) bit for bit
+            auto terms_side = [&](const float *__restrict__ d, const int *__restrict__ ix, const float *w, float *__restrict__ e, float *t_out,
+                                  int n, int n_max, bool vec) {
+                int k0 = 0;
+                if (vec && (e == nullptr || (reinterpret_cast<uintptr_t>(e) & 15u) == 0) && (reinterpret_cast<uintptr_t>(t_out) & 15u) == 0) {
+                    const float4 *d4 = reinterpret_cast<const float4 *>(d);
+                    const int4 *ix4 = reinterpret_cast<const int4 *>(ix);
+#pragma unroll 2
+                    for (int q = tid; q < (n >> 2); q += kDcdThreads) {
+                        const float4 dv = d4[q];
+                        const int4 iv = ix4[q];
+                        float4 ev;
+                        ev.x = __fmul_rn(expf(__fmul_rn(dv.x, neg_alpha)), w[iv.x]);
+                        ev.y = __fmul_rn(expf(__fmul_rn(dv.y, neg_alpha)), w[iv.y]);
+                        ev.z = __fmul_rn(expf(__fmul_rn(dv.z, neg_alpha)), w[iv.z]);
+                        ev.w = __fmul_rn(expf(__fmul_rn(dv.w, neg_alpha)), w[iv.w]);
+                        if (e) reinterpret_cast<float4 *>(e)[q] = ev;
+                        reinterpret_cast<float4 *>(t_out)[q] = make_float4(__fsub_rn(1.0f, ev.x), __fsub_rn(1.0f, ev.y), __fsub_rn(1.0f, ev.z),
+                                                                           __fsub_rn(1.0f, ev.w));
+                    }
+                    k0 = n & ~3;
+                }
+                for (int k = k0 + tid; k < n; k += kDcdThreads) {
+                    const float ewk = __fmul_rn(expf(__fmul_rn(d[k], neg_alpha)), w[ix[k]]);
+                    if (e) e[k] = ewk;
+                    t_out[k] = __fsub_rn(1.0f, ewk);
+                }
+                if (e) for (int k = n + tid; k < n_max; k += kDcdThreads) e[k] = 0.0f;   // past the valid length of a ragged cloud
+            };
+            terms_side(d1, i1, w1, out.ew1 ? out.ew1 + b * n1_max : nullptr, term, n1, n1_max, vd1);
+            terms_side(d2, i2, w2, out.ew2 ? out.ew2 + b * n2_max : nullptr, term + n1_max, n2, n2_max, vd2);
             __syncthreads();   // every weight has been read: the histogram space now takes the distances
         }
         float *sd = reinterpret_cast<float *>(hist);
-#pragma unroll 4
-        for (int k = tid; k < n1_max; k += kDcdThreads) sd[k] = d1[k];
-#pragma unroll 4
-        for (int k = tid; k < n2_max; k += kDcdThreads) sd[n1_max + k] = d2[k];
+        auto copy_side = [&](const float *__restrict__ d, float *dst, int n_max, bool vec) {
+            int k0 = 0;
+            if (vec && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+#pragma unroll 2
+                for (int q = tid; q < (n_max >> 2); q += kDcdThreads) reinterpret_cast<float4 *>(dst)[q] = reinterpret_cast<const float4 *>(d)[q];
+                k0 = n_max & ~3;
+            }
+            for (int k = k0 + tid; k < n_max; k += kDcdThreads) dst[k] = d[k];
+        };
+        copy_side(d1, sd, n1_max, vd1);
+        copy_side(d2, sd + n1_max, n2_max, vd2);
         __syncthreads();
     }
     auto ew_of = [&](float dk, int c, float frac) { return __fmul_rn(expf(__fmul_rn(-dk, alpha)), weight_of(c, frac)); };
@@ -745,7 +805,7 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
     if (what == 0) {
         if (want_loss) {
             if (STAGED) {
-                r = torch_row_sum([&](int k) { return sterm[k]; }, n, mis, lane);
+                r = torch_row_sum_staged<false>(sterm, n, mis, lane);
             } else {
                 r = torch_row_sum([&](int k) {
                         const float ewk = ew_of(d[k], cnt[ix[k]], frac);
@@ -756,10 +816,9 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
             }
         }
     } else if (what == 1) {
-        r = STAGED ? torch_row_sum([&](int k) { return sdist[k]; }, n, mis, lane) : torch_row_sum([&](int k) { return d[k]; }, n, mis, lane);
+        r = STAGED ? torch_row_sum_staged<false>(sdist, n, mis, lane) : torch_row_sum([&](int k) { return d[k]; }, n, mis, lane);
     } else if (what == 2) {
-        r = STAGED ? torch_row_sum([&](int k) { return sqrtf(sdist[k]); }, n, mis, lane)
-                   : torch_row_sum([&](int k) { return sqrtf(d[k]); }, n, mis, lane);
+        r = STAGED ? torch_row_sum_staged<true>(sdist, n, mis, lane) : torch_row_sum([&](int k) { return sqrtf(d[k]); }, n, mis, lane);
     } else if (out.fscore) {
         int c = 0;
         for (int k = lane; k < n; k += 32) c += (STAGED ? sdist[k] : d[k]) < out.f_threshold ? 1 : 0;
@@ -865,8 +924,8 @@ __global__ void __launch_bounds__(kGradThreads) grad_kernel(const GradParams p) 
 // scheduling (the reference's atomics and a shared-memory CAS loop both do).  Everything lives in shared memory:
 //   vec[(n1+n2)*3]  every point's own term g (p_own - p_nn)
 //   seg[n2 | n1]    segment ends after the counting sort (bins = points of the cloud being pointed AT)
-//   lst[n1 | n2]    the pointing points, grouped by the point they chose
-// Used when the pair fits (20 bytes per point) and neither cloud is broadcast over several pairs.
+//   lst[n1 | n2]    the pointing points (16-bit indices), grouped by the point they chose
+// Used when the pair fits (18 bytes per point) and neither cloud is broadcast over several pairs.
 constexpr int kGradSmemThreads = 512;
 constexpr int kGradSortMax = 32;  // longer lists (adversarial clouds: many points choosing one) are rebuilt by a linear scan
 
@@ -919,7 +978,8 @@ struct GradSide {
     float k_t, k_p, k_l, alpha;       // per-pair coefficients of cd_t, cd_p and the DCD loss (0 when not requested)
     int v_own;
 };
-__device__ __forceinline__ void grad_own_terms(const GradSide &sd, float *__restrict__ vec_own, int n_own, int *seg_bins, int *lst_own,
+typedef unsigned short grad_idx_t;   // a pair handled in shared memory has far fewer than 65 536 points per cloud
+__device__ __forceinline__ void grad_own_terms(const GradSide &sd, float *__restrict__ vec_own, int n_own, int *seg_bins, grad_idx_t *lst_own,
                                                bool file) {
     constexpr int U = 4;
     const int tid = threadIdx.x;
@@ -951,26 +1011,38 @@ __device__ __forceinline__ void grad_own_terms(const GradSide &sd, float *__rest
                 gx = __fmul_rn(g, __fsub_rn(ax[u], o[0]));
                 gy = __fmul_rn(g, __fsub_rn(ay[u], o[1]));
                 gz = __fmul_rn(g, __fsub_rn(az[u], o[2]));
-                if (file) lst_own[atomicAdd(&seg_bins[j2[u]], 1)] = j;
+                if (file) lst_own[atomicAdd(&seg_bins[j2[u]], 1)] = (grad_idx_t)j;
             }
             vec_own[j * 3 + 0] = gx; vec_own[j * 3 + 1] = gy; vec_own[j * 3 + 2] = gz;
         }
     }
 }
 
-// point j of one cloud: its own term minus, in ascending index order, the terms of the other cloud's points that chose it
+// point j of one cloud: its own term minus, in ascending index order, the terms of the other cloud's points that chose it.
+// Lists are short (a Poisson-like spread around one), but their lengths differ from lane to lane: up to four entries are
+// ordered by a branch-free sorting network and subtracted under predicates, so a warp does not serialise over its lanes'
+// different lengths; only longer lists take the data-dependent paths.
 __device__ __forceinline__ void grad_gather_side(const float *__restrict__ vec_own, const float *__restrict__ vec_oth, int n_own,
-                                                 const int *seg_bins, int *lst_oth, const int *idx_oth, int v_oth,
+                                                 const int *seg_bins, grad_idx_t *lst_oth, const int *idx_oth, int v_oth,
                                                  float *__restrict__ grad_out) {
+    constexpr int kNone = 0x7fffffff;
     for (int j = threadIdx.x; j < n_own; j += kGradSmemThreads) {
         const int start = j == 0 ? 0 : seg_bins[j - 1], end = seg_bins[j];
+        const int len = end - start;
         float ax = vec_own[j * 3 + 0], ay = vec_own[j * 3 + 1], az = vec_own[j * 3 + 2];
-        if (end - start == 1) {                                  // the common case: chosen by exactly one point
-            const int i = lst_oth[start];
-            ax = __fsub_rn(ax, vec_oth[i * 3 + 0]); ay = __fsub_rn(ay, vec_oth[i * 3 + 1]); az = __fsub_rn(az, vec_oth[i * 3 + 2]);
-        } else if (end - start <= kGradSortMax) {
+        if (len <= 4) {
+            int a0 = len > 0 ? (int)lst_oth[start] : kNone, a1 = len > 1 ? (int)lst_oth[start + 1] : kNone;
+            int a2 = len > 2 ? (int)lst_oth[start + 2] : kNone, a3 = len > 3 ? (int)lst_oth[start + 3] : kNone;
+#define URED_CSWAP(x, y) { const int lo_ = min(x, y), hi_ = max(x, y); x = lo_; y = hi_; }
+            URED_CSWAP(a0, a1) URED_CSWAP(a2, a3) URED_CSWAP(a0, a2) URED_CSWAP(a1, a3) URED_CSWAP(a1, a2)
+#undef URED_CSWAP
+            if (a0 != kNone) { ax = __fsub_rn(ax, vec_oth[a0 * 3 + 0]); ay = __fsub_rn(ay, vec_oth[a0 * 3 + 1]); az = __fsub_rn(az, vec_oth[a0 * 3 + 2]); }
+            if (a1 != kNone) { ax = __fsub_rn(ax, vec_oth[a1 * 3 + 0]); ay = __fsub_rn(ay, vec_oth[a1 * 3 + 1]); az = __fsub_rn(az, vec_oth[a1 * 3 + 2]); }
+            if (a2 != kNone) { ax = __fsub_rn(ax, vec_oth[a2 * 3 + 0]); ay = __fsub_rn(ay, vec_oth[a2 * 3 + 1]); az = __fsub_rn(az, vec_oth[a2 * 3 + 2]); }
+            if (a3 != kNone) { ax = __fsub_rn(ax, vec_oth[a3 * 3 + 0]); ay = __fsub_rn(ay, vec_oth[a3 * 3 + 1]); az = __fsub_rn(az, vec_oth[a3 * 3 + 2]); }
+        } else if (len <= kGradSortMax) {
             for (int u = start + 1; u < end; u++) {              // insertion sort of a short, thread-private segment
-                const int key = lst_oth[u];
+                const grad_idx_t key = lst_oth[u];
                 int w = u - 1;
                 while (w >= start && lst_oth[w] > key) { lst_oth[w + 1] = lst_oth[w]; w--; }
                 lst_oth[w + 1] = key;
@@ -988,7 +1060,7 @@ __device__ __forceinline__ void grad_gather_side(const float *__restrict__ vec_o
     }
 }
 
-__global__ void __launch_bounds__(kGradSmemThreads) grad_gather_kernel(const GradParams p) {
+__global__ void __launch_bounds__(kGradSmemThreads, 3) grad_gather_kernel(const GradParams p) {
     extern __shared__ float gsm[];
     __shared__ int scan_scratch[33];
     const size_t b = blockIdx.x;
@@ -996,7 +1068,7 @@ __global__ void __launch_bounds__(kGradSmemThreads) grad_gather_kernel(const Gra
     const int n1 = p.n[0], n2 = p.n[1], nt = n1 + n2;
     float *vec = gsm;                                   // [nt * 3]
     int *seg = reinterpret_cast<int *>(gsm + nt * 3);   // [n2 | n1]: bins over the points of cloud 2 (chosen by cloud 1), then over cloud 1
-    int *lst = seg + nt;                                // [n1 | n2]: cloud-1 points grouped by their choice, then cloud-2 points
+    grad_idx_t *lst = reinterpret_cast<grad_idx_t *>(seg + nt);   // [n1 | n2]: cloud-1 points grouped by their choice, then cloud-2 points
     const float *xyz1 = p.xyz[0] + b * n1 * 3, *xyz2 = p.xyz[1] + b * n2 * 3;
     const int *idx1 = p.idx[0] + b * n1, *idx2 = p.idx[1] ? p.idx[1] + b * n2 : nullptr;
     int v1 = valid_len(p.len[0], b, n1), v2 = valid_len(p.len[1], b, n2);
@@ -1551,7 +1623,7 @@ int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n
     p.alpha = alpha;
     p.len[0] = len1; p.len[1] = len2;
     p.one_dir = idx2 ? 0 : 1;   // (ured_nn_backward_one_direction passes no idx2)
-    const size_t smem_need = (size_t)(n1 + n2) * 20;  // own terms (12 B) + segment ends (4 B) + lists (4 B) per point
+    const size_t smem_need = (size_t)(n1 + n2) * 18;  // own terms (12 B) + segment ends (4 B) + lists (2 B) per point: 3 CTAs per SM at 2048 + 2048
     if (!shared1 && !shared2 && smem_need <= 200 * 1024 && !(flags_env_general())) {
         if (smem_need > kSmemOptIn)
             URED_CUDA(cudaFuncSetAttribute(grad_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "grad smem attribute");
