@@ -34,7 +34,7 @@ _SIGNATURES = {
     "ured_packed_bytes": (_sz, [_i, _i]),
     "ured_pack_clouds": (_i, [_p, _i, _i, _p, _p, _p]),
     "ured_nn_scratch_bytes": (_sz, [_i, _i, _i]),
-    "ured_nn_launch_shape": (_i, [_i, _i, _i, _u, _p, _p, _p, _p]),
+    "ured_nn_launch_shape": (_i, [_i, _i, _i, _u, _p, _p, _p, _p, _p, _p]),
     "ured_nn_packed": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _u, _p]),
     "ured_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
     "ured_chamfer_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _u, _p]),

@@ -184,12 +184,14 @@ struct NNParams {
     int np[2];
     int qtiles[2];  // query tiles per pair for direction 0 / 1
     int rep1, mod2;
-    // candidate splitting: with nsplit > 1 every (pair, direction, query tile) is cut into nsplit CTAs, each
-    // scanning a contiguous candidate range and writing its exact partial (d, idx) to part_*[split][B][n]
+    // candidate splitting: work items (pair, direction, query tile) [0, full_items) are scanned by one CTA each; the
+    // split_items items after them are cut into nsplit CTAs, each scanning a contiguous candidate range and writing its
+    // exact partial (d, idx) to part_*[split][split item][query of the tile].  Splitting only the LAST items of a launch
+    // (longest jobs first) fills the final, partly empty wave with short jobs.
     int nsplit;
-    int B;
-    float *part_dist[2];
-    int *part_idx[2];
+    int full_items, split_items;
+    float *part_dist;
+    int *part_idx;
     const int *len[2];  // optional valid point counts per cloud-1 / cloud-2 entry (ragged batches)
 };
 
@@ -213,11 +215,16 @@ __global__ void __launch_bounds__(T, MINB) nn_kernel(const NNParams p) {
 
     const int tid = threadIdx.x;
     // ---- work item: (pair b, direction, query tile) --------------------------------------
-    const int per_pair = (p.qtiles[0] + p.qtiles[1]) * p.nsplit;
-    const int b = blockIdx.x / per_pair;
-    const int rem0 = blockIdx.x - b * per_pair;
-    const int sp = rem0 % p.nsplit;  // candidate split handled by this CTA
-    const int rem = rem0 / p.nsplit;
+    int item = blockIdx.x, sp = 0, nsplit = 1;   // sp: candidate split handled by this CTA
+    if ((int)blockIdx.x >= p.full_items) {
+        const int r0 = blockIdx.x - p.full_items;
+        item = p.full_items + r0 / p.nsplit;
+        sp = r0 % p.nsplit;
+        nsplit = p.nsplit;
+    }
+    const int per_pair = p.qtiles[0] + p.qtiles[1];
+    const int b = item / per_pair;
+    const int rem = item - b * per_pair;
     const int dir = rem >= p.qtiles[0] ? 1 : 0;
     const int qt = dir ? rem - p.qtiles[0] : rem;
     const int c1 = b / p.rep1, c2 = b % p.mod2;
@@ -230,24 +237,31 @@ __global__ void __launch_bounds__(T, MINB) nn_kernel(const NNParams p) {
     const int nc = len_c ? max(0, min(len_c[cc], dir ? p.n[0] : p.n[1])) : (dir ? p.n[0] : p.n[1]);  // valid candidates
     const int ncp = (nc + kChunk - 1) / kChunk * kChunk;
     const float *__restrict__ qxyz = (dir ? p.xyz[1] : p.xyz[0]) + (size_t)cq * nq * 3;
+    // queries come from the query cloud's own packed image when there is one (three coalesced loads; the raw cloud need
+    // not exist any more), otherwise from the raw [n, 3] rows (one-direction calls pack only the candidate side)
+    const int nqp_max = dir ? p.np[1] : p.np[0];
+    const float *__restrict__ qsoa = (dir ? p.soa[1] : p.soa[0]);
+    if (qsoa) qsoa += (size_t)cq * ((size_t)nqp_max * 4 + kPackTail);
     const float *__restrict__ csoa = (dir ? p.soa[0] : p.soa[1]) + (size_t)cc * ((size_t)ncp_max * 4 + kPackTail);
 
-    float *out_d = p.nsplit == 1 ? (dir ? p.dist[1] : p.dist[0]) + (size_t)b * nq
-                                 : (dir ? p.part_dist[1] : p.part_dist[0]) + ((size_t)sp * p.B + b) * nq;
-    int *out_i = p.nsplit == 1 ? (dir ? p.idx[1] : p.idx[0]) + (size_t)b * nq
-                               : (dir ? p.part_idx[1] : p.part_idx[0]) + ((size_t)sp * p.B + b) * nq;
+    // unsplit items write the final arrays at the query's index j; split items write partials at the query's slot in the tile
+    const bool split = nsplit > 1;
+    const size_t part_base = ((size_t)sp * p.split_items + (item - p.full_items)) * QT;
+    float *out_d = split ? p.part_dist + part_base : (dir ? p.dist[1] : p.dist[0]) + (size_t)b * nq;
+    int *out_i = split ? p.part_idx + part_base : (dir ? p.idx[1] : p.idx[0]) + (size_t)b * nq;
+    const int out_shift = split ? qt * QT : 0;   // out index = j - out_shift
     if (qt * QT >= nq_v || nc == 0) {
         // nothing to search: the reference kernel leaves its zero-filled outputs untouched in this case
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int j = (qt * R + r) * T + tid;
-            if (j < nq) { out_d[j] = 0.0f; out_i[j] = 0; }
+            if (j < nq) { out_d[j - out_shift] = 0.0f; out_i[j - out_shift] = 0; }
         }
         return;
     }
 
     // candidate range of this split, in whole 32-candidate chunks
-    const int chunks_per_split = (ncp / kChunk + p.nsplit - 1) / p.nsplit;
+    const int chunks_per_split = (ncp / kChunk + nsplit - 1) / nsplit;
     const int k_lo = min(ncp, sp * chunks_per_split * kChunk);
     const int k_hi = min(ncp, k_lo + chunks_per_split * kChunk);
 
@@ -285,7 +299,8 @@ __global__ void __launch_bounds__(T, MINB) nn_kernel(const NNParams p) {
     for (int r = 0; r < R; r++) {
         int j = (qt * R + r) * T + tid;
         j = j < nq_v ? j : nq_v - 1;
-        qx[r] = kScale * qxyz[j * 3 + 0]; qy[r] = kScale * qxyz[j * 3 + 1]; qz[r] = kScale * qxyz[j * 3 + 2];
+        if (qsoa) { qx[r] = kScale * qsoa[j]; qy[r] = kScale * qsoa[nqp_max + j]; qz[r] = kScale * qsoa[2 * nqp_max + j]; }
+        else { qx[r] = kScale * qxyz[j * 3 + 0]; qy[r] = kScale * qxyz[j * 3 + 1]; qz[r] = kScale * qxyz[j * 3 + 2]; }
         best[r] = kInf; second[r] = kInf; bchunk[r] = k_lo;
     }
 
@@ -488,9 +503,9 @@ __global__ void __launch_bounds__(T, MINB) nn_kernel(const NNParams p) {
         const int j = (qt * R + it + u) * T + tid;
         if (j < nq) {
             if (j >= nq_v) { bd = 0.0f; bi = 0; }                          // past the valid length of a ragged cloud
-            else if (p.nsplit > 1 && k_lo >= k_hi) bd = kInf;              // empty split: loses every merge
-            out_d[j] = bd;
-            out_i[j] = bi;
+            else if (split && k_lo >= k_hi) bd = kInf;                     // empty split: loses every merge
+            out_d[j - out_shift] = bd;
+            out_i[j - out_shift] = bi;
         }
       }
       if (R > U) {
@@ -505,31 +520,36 @@ __global__ void __launch_bounds__(T, MINB) nn_kernel(const NNParams p) {
 
 // Merge of the per-split partial results: splits cover ascending candidate ranges, so a strict '<' in split
 // order keeps the lowest index among equal distances -- the same rule as the reference's tile merge (chamfer3D.cu:126).
-// One launch covers both directions: elements [0, total1) belong to direction 0, the rest to direction 1.
+// One thread per (split item, query slot of its tile); both directions in one launch.
 struct MergeParams {
-    const float *pd[2];
-    const int *pi[2];
+    const float *pd;
+    const int *pi;
     float *dist[2];
     int *idx[2];
-    size_t total[2];
-    int nsplit;
+    int n[2], qtiles[2];
+    int nsplit, full_items, split_items, QT;
 };
 __global__ void __launch_bounds__(256) merge_splits_kernel(const MergeParams m) {
-    size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
-    const int dir = t >= m.total[0] ? 1 : 0;
-    if (dir) t -= m.total[0];
-    const size_t total = dir ? m.total[1] : m.total[0];
-    if (t >= total) return;
-    const float *__restrict__ pd = dir ? m.pd[1] : m.pd[0];
-    const int *__restrict__ pi = dir ? m.pi[1] : m.pi[0];
-    float d = pd[t];
-    int i = pi[t];
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t per_split = (size_t)m.split_items * m.QT;
+    if (t >= per_split) return;
+    const int titem = (int)(t / m.QT), l = (int)(t - (size_t)titem * m.QT);
+    const int item = m.full_items + titem;
+    const int per_pair = m.qtiles[0] + m.qtiles[1];
+    const int b = item / per_pair, rem = item - b * per_pair;
+    const int dir = rem >= m.qtiles[0] ? 1 : 0;
+    const int qt = dir ? rem - m.qtiles[0] : rem;
+    const int nq = dir ? m.n[1] : m.n[0];
+    const int j = qt * m.QT + l;
+    if (j >= nq) return;
+    float d = m.pd[t];
+    int i = m.pi[t];
     for (int s = 1; s < m.nsplit; s++) {
-        const float ds = pd[s * total + t];
-        if (ds < d) { d = ds; i = pi[s * total + t]; }
+        const float ds = m.pd[s * per_split + t];
+        if (ds < d) { d = ds; i = m.pi[s * per_split + t]; }
     }
-    (dir ? m.dist[1] : m.dist[0])[t] = d;
-    (dir ? m.idx[1] : m.idx[0])[t] = i;
+    (dir ? m.dist[1] : m.dist[0])[(size_t)b * nq + j] = d;
+    (dir ? m.idx[1] : m.idx[0])[(size_t)b * nq + j] = i;
 }
 
 // Launch shape: a kernel variant (T threads x R queries per thread, MINB resident CTAs per SM) and nsplit candidate
@@ -553,7 +573,7 @@ const NNVariant kVariants[kNumVariants] = {
     {4, 64, 8},    // 7
 };
 constexpr int kDefaultVariant = 0, kSmallVariant = 5;
-struct NNShape { int variant; int R, T; int nsplit; };
+struct NNShape { int variant; int R, T; int nsplit; bool split_all; };
 
 inline long long nn_items(int B, int n1, int n2, int qt) {
     return (long long)B * ((n1 + qt - 1) / qt + (n2 + qt - 1) / qt);
@@ -576,8 +596,35 @@ NNShape choose_nn_shape(int B, int n1, int n2, bool exact) {
     while (ns < 8 && cand / (ns * 2) >= 2048) ns *= 2;                                        // 2048-candidate ranges
     while (ns < 8 && ns * 2 <= max_split && nn_items(B, n1, n2, qt) * ns * 10 < 17 * kSMs) ns *= 2;  // fill the machine
     if (forced_s > 0) { ns = 1; while (ns < forced_s && ns < 8 && ns * 2 <= max_split) ns *= 2; }
-    NNShape sh = {v, kVariants[v].R, kVariants[v].T, ns};
+    NNShape sh = {v, kVariants[v].R, kVariants[v].T, ns, ns > 1};
+    if (ns == 1 && env_int("URED_NN_TAIL_SPLIT", 1)) {   // the tail rule below may still split the last items (split_plan)
+        int t = 1;
+        while (t < 4 && t * 2 <= max_split) t *= 2;
+        sh.nsplit = t;
+    }
     return sh;
+}
+
+// Which items of a launch of `items` equal work items are split.  split_all: every item (chosen above).  Otherwise, when
+// the launch is a few waves long and its last wave is only partly full, the items of that last wave are cut into
+// candidate ranges: the block scheduler hands out CTAs in index order, so the long (unsplit) jobs run first and the
+// short ones fill the machine at the end instead of leaving most SMs with one or two CTAs (cfg3 shard of 125 shapes:
+// 1000 items on 740 slots).
+struct SplitPlan { int full_items, split_items, nsplit; };
+SplitPlan split_plan(const NNShape &sh, long long items) {
+    SplitPlan pl = {(int)items, 0, 1};
+    if (sh.split_all) { pl.full_items = 0; pl.split_items = (int)items; pl.nsplit = sh.nsplit; return pl; }
+    if (sh.nsplit < 2) return pl;
+    const long long slots = 148ll * kVariants[sh.variant].minb;
+    const long long frac = items % slots;
+    if (items > slots && items < 4 * slots && frac * 16 > slots && frac * 5 < slots * 4) {
+        pl.split_items = (int)frac; pl.full_items = (int)(items - frac); pl.nsplit = sh.nsplit;
+    }
+    return pl;
+}
+size_t split_scratch_bytes(const NNShape &sh, long long items) {
+    const SplitPlan pl = split_plan(sh, items);
+    return pl.split_items ? align_up((size_t)pl.nsplit * pl.split_items * (size_t)(sh.R * sh.T) * 8, 256) : 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1386,7 +1433,8 @@ template <bool SCREEN, int R, int T, int MINB, bool PF = false>
 int launch_nn(const NNParams &p, int B, cudaStream_t st) {
     constexpr int NARR = SCREEN ? 4 : 3;
     const size_t smem = (size_t)kStages * NARR * kTile * sizeof(float);
-    const long long grid = (long long)B * (p.qtiles[0] + p.qtiles[1]) * p.nsplit;
+    const long long grid = (long long)p.full_items + (long long)p.split_items * p.nsplit;
+    (void)B;
     if (grid > 0x7fffffffll) return fail_arg(URED_E_SHAPE, "too many work items for one launch");
     nn_kernel<SCREEN, R, T, MINB, PF><<<(unsigned)grid, T, smem, st>>>(p);
     URED_COUNT_LAUNCH();
@@ -1440,18 +1488,32 @@ int ured_pack_clouds(const float *xyz, int count, int n, const int *len, void *p
 
 size_t ured_nn_scratch_bytes(int B, int n1, int n2) {
     if (B <= 0 || n1 <= 0 || n2 <= 0) return 0;
-    const int a = choose_nn_shape(B, n1, n2, false).nsplit, b = choose_nn_shape(B, n1, n2, true).nsplit;
-    const int nsplit = a > b ? a : b;  // the caller need not know which kernel flavour will run
-    return nsplit > 1 ? align_up((size_t)nsplit * B * ((size_t)n1 + n2) * 8, 256) : 0;
+    // the caller need not know which kernel flavour (screen / exact, one or two directions) will run: the largest need of the four
+    size_t need = 0;
+    for (int exact = 0; exact < 2; exact++) {
+        const NNShape sh = choose_nn_shape(B, n1, n2, exact != 0);
+        const int qt = sh.R * sh.T;
+        const long long two = nn_items(B, n1, n2, qt), one = (long long)B * ((n1 + qt - 1) / qt);
+        const size_t a = split_scratch_bytes(sh, two), b = split_scratch_bytes(sh, one);
+        need = a > need ? a : need;
+        need = b > need ? b : need;
+    }
+    return need;
 }
 
-int ured_nn_launch_shape(int B, int n1, int n2, unsigned flags, int *variant, int *queries_per_cta, int *threads, int *nsplit) {
+int ured_nn_launch_shape(int B, int n1, int n2, unsigned flags, int *variant, int *queries_per_cta, int *threads, int *nsplit,
+                         int *items, int *split_items) {
     if (B <= 0 || n1 <= 0 || n2 <= 0) return fail_arg(URED_E_SHAPE, "ured_nn_launch_shape: empty problem");
     const NNShape sh = choose_nn_shape(B, n1, n2, (flags & URED_FLAG_EXACT_ONLY) != 0);
+    const int qt = sh.R * sh.T;
+    const long long n_items = (long long)B * ((n1 + qt - 1) / qt + ((flags & URED_FLAG_ONE_DIRECTION) ? 0 : (n2 + qt - 1) / qt));
+    const SplitPlan pl = split_plan(sh, n_items);
     if (variant) *variant = sh.variant;
-    if (queries_per_cta) *queries_per_cta = sh.R * sh.T;
+    if (queries_per_cta) *queries_per_cta = qt;
     if (threads) *threads = sh.T;
-    if (nsplit) *nsplit = sh.nsplit;
+    if (nsplit) *nsplit = pl.split_items ? pl.nsplit : 1;
+    if (items) *items = (int)n_items;
+    if (split_items) *split_items = pl.split_items;
     return 0;
 }
 
@@ -1470,11 +1532,12 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
         if (n2 && !skip2) { URED_CUDA(cudaMemsetAsync(dist2, 0, (size_t)B * n2 * 4, st), "memset"); URED_CUDA(cudaMemsetAsync(idx2, 0, (size_t)B * n2 * 4, st), "memset"); }
         return 0;
     }
-    if (!xyz1 || !xyz2 || (!packed1 && !skip2) || !packed2) return fail_arg(URED_E_NULL, "ured_nn_packed: NULL input");
+    // candidates: packed2 always, packed1 unless one direction only; queries: the packed image if given, else the raw cloud
+    if ((!packed1 && (!skip2 || !xyz1)) || !packed2) return fail_arg(URED_E_NULL, "ured_nn_packed: NULL input");
     PackedView v1 = view_packed(packed1, n1), v2 = view_packed(packed2, n2);
     NNParams p;
     p.xyz[0] = xyz1; p.xyz[1] = xyz2;
-    p.soa[0] = v1.soa; p.soa[1] = v2.soa;
+    p.soa[0] = packed1 ? v1.soa : nullptr; p.soa[1] = v2.soa;
     p.dist[0] = dist1; p.dist[1] = dist2;
     p.idx[0] = idx1; p.idx[1] = idx2;
     p.n[0] = n1; p.n[1] = n2;
@@ -1487,32 +1550,30 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
     const bool one_dir = (flags & URED_FLAG_ONE_DIRECTION) != 0;  // only cloud-1 points search cloud 2 (K=1 kNN)
     p.qtiles[0] = (n1 + QT - 1) / QT;
     p.qtiles[1] = one_dir ? 0 : (n2 + QT - 1) / QT;
-    p.nsplit = sh.nsplit;
-    p.B = B;
-    const size_t tot1 = (size_t)B * n1, tot2 = (size_t)B * n2;
-    if (sh.nsplit > 1) {
+    const long long items = (long long)B * (p.qtiles[0] + p.qtiles[1]);
+    if (items > 0x7fffffffll / 8) return fail_arg(URED_E_SHAPE, "too many work items for one launch");
+    const SplitPlan pl = split_plan(sh, items);
+    p.nsplit = pl.nsplit; p.full_items = pl.full_items; p.split_items = pl.split_items;
+    p.part_dist = nullptr; p.part_idx = nullptr;
+    if (pl.split_items) {
+        const size_t need = split_scratch_bytes(sh, items);
         if (!scratch) return fail_arg(URED_E_NULL, "ured_nn_packed: scratch buffer required for this shape (ured_nn_scratch_bytes)");
-        if ((uintptr_t)scratch % 256 || scratch_bytes < ured_nn_scratch_bytes(B, n1, n2))
-            return fail_arg(URED_E_WORKSPACE, "ured_nn_packed: scratch too small or misaligned");
-        // [dist1 parts | dist2 parts | idx1 parts | idx2 parts]
-        p.part_dist[0] = (float *)scratch;
-        p.part_dist[1] = p.part_dist[0] + sh.nsplit * tot1;
-        p.part_idx[0] = (int *)(p.part_dist[1] + sh.nsplit * tot2);
-        p.part_idx[1] = p.part_idx[0] + sh.nsplit * tot1;
-    } else {
-        p.part_dist[0] = p.part_dist[1] = nullptr;
-        p.part_idx[0] = p.part_idx[1] = nullptr;
+        if ((uintptr_t)scratch % 256 || scratch_bytes < need) return fail_arg(URED_E_WORKSPACE, "ured_nn_packed: scratch too small or misaligned");
+        // [dist parts | idx parts], each [split][split item][query slot of the tile]
+        p.part_dist = (float *)scratch;
+        p.part_idx = (int *)(p.part_dist + (size_t)pl.nsplit * pl.split_items * QT);
     }
     rc = launch_nn_variant(sh.variant, exact, p, B, st);
-    if (rc || sh.nsplit == 1) return rc;
+    if (rc || pl.split_items == 0) return rc;
     MergeParams mp;
-    mp.pd[0] = p.part_dist[0]; mp.pd[1] = p.part_dist[1];
-    mp.pi[0] = p.part_idx[0]; mp.pi[1] = p.part_idx[1];
+    mp.pd = p.part_dist; mp.pi = p.part_idx;
     mp.dist[0] = dist1; mp.dist[1] = dist2;
     mp.idx[0] = idx1; mp.idx[1] = idx2;
-    mp.total[0] = tot1; mp.total[1] = one_dir ? 0 : tot2;
-    mp.nsplit = sh.nsplit;
-    merge_splits_kernel<<<(unsigned)((mp.total[0] + mp.total[1] + 255) / 256), 256, 0, st>>>(mp);
+    mp.n[0] = n1; mp.n[1] = n2;
+    mp.qtiles[0] = p.qtiles[0]; mp.qtiles[1] = p.qtiles[1];
+    mp.nsplit = pl.nsplit; mp.full_items = pl.full_items; mp.split_items = pl.split_items; mp.QT = QT;
+    const size_t threads = (size_t)pl.split_items * QT;
+    merge_splits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(mp);
     URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "merge_splits_kernel launch");
 }

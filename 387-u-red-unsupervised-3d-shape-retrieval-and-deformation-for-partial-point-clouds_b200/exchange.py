@@ -123,8 +123,8 @@ class PeerExchange:
         if not scores.is_cuda:
             raise RuntimeError("PeerExchange.topk: GPU tensors only")
         scores = scores.contiguous().float()
-        out_s = torch.empty(self.rows, self.k, device=scores.device, dtype=torch.float32)
-        out_i = torch.empty(self.rows, self.k, device=scores.device, dtype=torch.int32)
+        both = torch.empty(2, self.rows, self.k, device=scores.device, dtype=torch.int32)   # one buffer: [0] score bits, [1] ids
+        out_s, out_i = both[0].view(torch.float32), both[1]
         with torch.cuda.device(scores.device):
             rc = self.lib.ured_topk_exchange(_native.ptr(scores) if scores.numel() else None, self.rows, scores.shape[1], self.k,
                                              int(idx_offset), self._table, self.world, self.rank, self.rows,

@@ -44,7 +44,25 @@ class PackedClouds:
 
     @property
     def device(self):
-        return self.xyz.device
+        return self.packed.device
+
+    def repack_(self, xyz):
+        """Pack new clouds of the same shape into this image's storage (in place, one kernel, on the current stream).
+
+        After this the image no longer refers to a raw tensor (``self.xyz`` is None): the nearest-neighbour kernel reads
+        queries and candidates from the image alone, so the caller's ``xyz`` may be freed or overwritten right away.
+        Used by the retrieval engine: the image is a static buffer of its CUDA graph, the targets arrive in user tensors.
+        """
+        if tuple(xyz.shape) != (self.count, self.n, 3):
+            raise ValueError(f"repack_ needs clouds of shape {(self.count, self.n, 3)}, got {tuple(xyz.shape)}")
+        _require_cloud("xyz", xyz)
+        xyz = xyz.contiguous()
+        lib = _native.load()
+        with torch.cuda.device(self.packed.device):
+            rc = lib.ured_pack_clouds(_native.ptr(xyz), self.count, self.n, None, _native.ptr(self.packed), _stream(self.packed.device))
+        _native.check(rc, "ured_pack_clouds")
+        self.xyz = None
+        return self
 
     @property
     def block_bytes(self):
@@ -55,7 +73,7 @@ class PackedClouds:
         if not (0 <= lo <= hi <= self.count):
             raise IndexError(f"slice [{lo}, {hi}) outside [0, {self.count})")
         view = object.__new__(PackedClouds)
-        view.xyz = self.xyz[lo:hi]
+        view.xyz = self.xyz[lo:hi] if self.xyz is not None else None
         view.count, view.n = hi - lo, self.n
         view.packed = self.packed[lo * self.block_bytes:]
         return view
@@ -358,7 +376,7 @@ class RetrievalEngine:
 
     def _scores(self, targets):
         if self.lib is None or self.lib.count == 0:
-            return torch.empty(self.Q, 0, device=targets.device, dtype=torch.float32)
+            return torch.empty(self.Q, 0, device=targets.device, dtype=torch.float32)   # (targets: a tensor or a PackedClouds)
         return score_library(targets, self.lib, alpha=self.alpha, n_lambda=self.n_lambda, max_pairs=self.max_pairs,
                              exact_ranking=self.exact_ranking, metrics=(self.metric,))[self.metric]
 
@@ -391,8 +409,12 @@ class RetrievalEngine:
             raise ValueError(f"engine was built for {self.Q} queries per call")
         if not self.use_graph:
             return self._pipeline(targets.float())
+        targets = targets.float()
         if self.graph is None:
-            self.static_in = targets.float().contiguous().clone()
+            # the graph's static input is the targets' PACKED image: every query packs the caller's tensor straight into it
+            # (one kernel, no staging copy) and the captured kernels read queries and candidates from the image alone
+            self.static_in = PackedClouds(targets.contiguous())
+            self.static_in.xyz = None
             if self.exchange == "peer":
                 self._peer(targets.device)          # buffer mapping (collective set-up) happens outside the capture
             side = torch.cuda.Stream(device=targets.device)
@@ -406,9 +428,13 @@ class RetrievalEngine:
             n0 = _native.load().ured_kernel_launches()
             with torch.cuda.graph(self.graph):
                 self.static_out = self._pipeline(self.static_in)
-            self.kernels_per_replay = int(_native.load().ured_kernel_launches() - n0)  # library kernels inside the graph
-        self.static_in.copy_(targets, non_blocking=True)
+            self.kernels_per_replay = int(_native.load().ured_kernel_launches() - n0) + 1  # library kernels per query (graph + the pack)
+        self.static_in.repack_(targets)
         self.graph.replay()
+        base = self.static_out[0]._base
+        if base is not None and base is self.static_out[1]._base:   # both outputs live in one buffer: one copy instead of two
+            both = base.clone()
+            return both[0].view(torch.float32), both[1]
         return tuple(t.clone() for t in self.static_out)
 
     def check(self):

@@ -284,8 +284,8 @@ def nn_roofline(ctx, x_dev, gt_dev, B, n_x, n_gt, steps, warmup, exact_only, pea
         ured._native.check(rc, "ured_nn_packed")
 
     ms_nn, _ = ctx.timed(nn_only, steps, warmup)
-    v, q, t, ns = (ctypes.c_int() for _ in range(4))
-    lib.ured_nn_launch_shape(B, n_gt, n_x, flags, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns))
+    v, q, t, ns, it, si = (ctypes.c_int() for _ in range(6))
+    lib.ured_nn_launch_shape(B, n_gt, n_x, flags, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns), ctypes.byref(it), ctypes.byref(si))
     pairs = 2.0 * B * n_x * n_gt
     flop = FLOP_PER_PAIR * pairs
     achieved = flop / (ms_nn * 1e-3) / 1e12
@@ -304,7 +304,8 @@ def nn_roofline(ctx, x_dev, gt_dev, B, n_x, n_gt, steps, warmup, exact_only, pea
             "measured_ffma_peak": ffma_peak, "frac_of_measured_ffma_peak": (achieved / ffma_peak) if ffma_peak else None,
             "measured_ffma_peak_source": "ured_probe_ffma (pure FFMA stream) timed in this run, best of 5",
             "flop_per_launch": flop, "kernel_ms": ms_nn, "tpair_per_s": pairs / (ms_nn * 1e-3) / 1e12,
-            "launch_shape": {"variant": v.value, "queries_per_cta": q.value, "threads": t.value, "candidate_splits": ns.value},
+            "launch_shape": {"variant": v.value, "queries_per_cta": q.value, "threads": t.value, "work_items": it.value,
+                             "split_items": si.value, "candidate_splits": ns.value},
             "note": "FLOP-accounted at the reference's 8 FLOP per ordered pair; the screening variant executes 6 FLOP per pair in its main loop "
                     "(executed-FLOP fraction = 0.75 x frac)"}
 

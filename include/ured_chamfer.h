@@ -89,18 +89,24 @@ int ured_pack_clouds(const float *xyz, int count, int n, const int *len, void *p
 /* ---- nearest neighbours on packed clouds (both directions, one launch) --------------------
  * dist1/idx1: [B, n1]  for every point of cloud 1, squared distance to / index of its nearest
  *                      point in cloud 2 (lowest index on ties);  dist2/idx2: [B, n2] vice versa.
+ * Queries are read from the packed images too, so xyz1 / xyz2 may be NULL when the corresponding image is given
+ * (xyz1 is needed only with URED_FLAG_ONE_DIRECTION and packed1 == NULL).
  * Results are bit-identical to NmDistanceKernel (chamfer3D.cu:12-134) for finite inputs.  Non-finite coordinates:
  * memory-safe (indices stay in range) but unspecified -- the reference admits a NaN distance only as the first
  * candidate of each of its 512-candidate tiles (chamfer3D.cu:36,126), an artefact this library does not reproduce;
  * the Python layer offers an opt-in check that raises instead (URED_CHECK_FINITE=1).
  *
- * For shapes whose grid would be too small (few pairs, or very large clouds) the candidate range is split over
- * several CTAs and merged afterwards; that needs `scratch`: ured_nn_scratch_bytes(B, n1, n2) bytes (0 for most
- * shapes, in which case scratch may be NULL), 256-byte aligned. */
+ * For shapes whose grid would be too small (few pairs), very large clouds, and launches whose last wave of CTAs would
+ * be mostly empty, the candidate range of some or all work items is split over several CTAs and merged afterwards;
+ * that needs `scratch`: ured_nn_scratch_bytes(B, n1, n2) bytes (0 for most shapes, in which case scratch may be
+ * NULL), 256-byte aligned. */
 size_t ured_nn_scratch_bytes(int B, int n1, int n2);
-/* The launch shape ured_nn_packed will use for this problem (reporting / tests): kernel variant id, queries per CTA,
- * threads per CTA and the number of candidate splits.  Any output pointer may be NULL. */
-int ured_nn_launch_shape(int B, int n1, int n2, unsigned flags, int *variant, int *queries_per_cta, int *threads, int *nsplit);
+/* The launch plan ured_nn_packed will use for this problem (reporting / tests): kernel variant id, queries per CTA,
+ * threads per CTA, the number of work items (pair, direction, query tile), how many of them -- always the LAST ones of
+ * the launch -- are cut into `nsplit` candidate ranges, and nsplit itself (1 when nothing is split).  Any output
+ * pointer may be NULL. */
+int ured_nn_launch_shape(int B, int n1, int n2, unsigned flags, int *variant, int *queries_per_cta, int *threads, int *nsplit,
+                         int *items, int *split_items);
 int ured_nn_packed(const float *xyz1, const void *packed1, int n1,
                    const float *xyz2, const void *packed2, int n2,
                    int B, int rep1, int mod2, const int *len1, const int *len2,

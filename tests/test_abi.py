@@ -34,7 +34,7 @@ def test_abi_version_and_sizes(ured):
     assert lib.ured_packed_bytes(2, 2048) == 2 * (4 * 2048 + 32) * 4
     assert lib.ured_packed_bytes(1, 100) == (4 * 128 + 32) * 4 + 128  # padded to 32 points, rounded up to 256 bytes
     assert lib.ured_chamfer_workspace_bytes(3, 100, 200) == lib.ured_packed_bytes(3, 100) + lib.ured_packed_bytes(3, 200) + lib.ured_nn_scratch_bytes(3, 100, 200)
-    assert lib.ured_nn_scratch_bytes(640, 2048, 2048) == 0            # enough pairs: no candidate splitting
+    assert lib.ured_nn_scratch_bytes(5000, 2048, 2048) == 0           # many waves of CTAs (in either call flavour): no candidate splitting
     assert lib.ured_nn_scratch_bytes(16, 16384, 16384) == 8 * 16 * 32768 * 8  # dense clouds: 8 splits (2048-candidate ranges) of partial (d, idx)
 
 
@@ -82,28 +82,33 @@ def test_header_is_plain_c(tmp_path):
 
 
 def test_launch_shape_heuristic_invariants(ured):
-    """ured_nn_launch_shape / ured_nn_scratch_bytes expose the launch choice: 1, 2, 4 or 8 candidate splits, never below 512
-    candidates per split, clouds of >= 4096 candidates cut into ranges of >= 2048, no split for mid-size clouds once the grid
-    fills the machine, and the scratch / workspace formulas consistent with it."""
+    """ured_nn_launch_shape / ured_nn_scratch_bytes expose the launch plan: 1, 2, 4 or 8 candidate splits, never below 512
+    candidates per split, clouds of >= 4096 candidates cut into ranges of >= 2048, only the last partial wave split for
+    mid-size launches, nothing split once the grid is many waves long, scratch consistent with the plan."""
     import ctypes
     lib = ured._native.load()
-    for B in [1, 2, 7, 16, 32, 100, 640, 5000]:
+    for B in [1, 2, 7, 16, 32, 100, 125, 640, 5000]:
         for n1, n2 in [(1, 1), (100, 200), (511, 4096), (1024, 1024), (2048, 2048), (2000, 1000), (16384, 16384), (4096, 100000)]:
-            v, q, t, ns = (ctypes.c_int() for _ in range(4))
-            assert lib.ured_nn_launch_shape(B, n1, n2, 0, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns)) == 0
+            v, q, t, ns, items, split = (ctypes.c_int() for _ in range(6))
+            assert lib.ured_nn_launch_shape(B, n1, n2, 0, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns),
+                                            ctypes.byref(items), ctypes.byref(split)) == 0
             nsplit = ns.value
             sb = lib.ured_nn_scratch_bytes(B, n1, n2)
-            per_split = B * (n1 + n2) * 8
             assert nsplit in (1, 2, 4, 8) and q.value % t.value == 0 and q.value in (256, 512, 1024)
-            if nsplit == 1:
-                assert sb == 0
-            else:
-                assert sb % 256 == 0 and 0 <= sb - nsplit * per_split < 256
+            assert items.value == B * (-(-n1 // q.value) + -(-n2 // q.value)) and 0 <= split.value <= items.value
+            assert (split.value == 0) == (nsplit == 1)
+            assert sb % 256 == 0 and sb >= (nsplit * split.value * q.value * 8 if split.value else 0)
+            if nsplit > 1:
                 assert min(n1, n2) // nsplit >= 512                       # a split never gets fewer than 512 candidates
-            items = B * (-(-n1 // q.value) + -(-n2 // q.value))
-            if min(n1, n2) < 4096 and items >= 148 * 2:
-                assert nsplit == 1                                        # enough CTAs already: no splitting
-            if min(n1, n2) >= 4096 and items * nsplit >= 148 * 2:
-                assert min(n1, n2) // nsplit >= 2048 or nsplit == 8       # big clouds: 2048-candidate ranges
+            if min(n1, n2) < 4096 and items.value >= 148 * 5 * 4:
+                assert split.value == 0                                   # many waves of CTAs: no splitting at all
+            if min(n1, n2) < 4096 and 148 * 2 <= items.value and split.value:
+                assert split.value < 148 * 5 and nsplit <= 4              # mid-size launch: only the last partial wave is cut
+            if min(n1, n2) >= 4096 and items.value * nsplit >= 148 * 2:
+                assert split.value == items.value and (min(n1, n2) // nsplit >= 2048 or nsplit == 8)   # big clouds: 2048-candidate ranges
             assert lib.ured_chamfer_workspace_bytes(B, n1, n2) == lib.ured_packed_bytes(B, n1) + lib.ured_packed_bytes(B, n2) + sb
+    # the cfg3 shard of 125 shapes: 1000 work items on 740 CTA slots -> the last 260 are split
+    v, q, t, ns, items, split = (ctypes.c_int() for _ in range(6))
+    lib.ured_nn_launch_shape(125, 2048, 2048, 0, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns), ctypes.byref(items), ctypes.byref(split))
+    assert (items.value, split.value, ns.value) == (1000, 260, 4)
     assert lib.ured_nn_scratch_bytes(0, 8, 8) == 0 and lib.ured_nn_scratch_bytes(4, 0, 8) == 0
