@@ -597,7 +597,10 @@ NNShape choose_nn_shape(int B, int n1, int n2, bool exact) {
     while (ns < 8 && ns * 2 <= max_split && nn_items(B, n1, n2, qt) * ns * 10 < 17 * kSMs) ns *= 2;  // fill the machine
     if (forced_s > 0) { ns = 1; while (ns < forced_s && ns < 8 && ns * 2 <= max_split) ns *= 2; }
     NNShape sh = {v, kVariants[v].R, kVariants[v].T, ns, ns > 1};
-    if (ns == 1 && env_int("URED_NN_TAIL_SPLIT", 1)) {   // the tail rule below may still split the last items (split_plan)
+    // Tail rule (split_plan): measured on B200 it does NOT pay -- the 260-item tail of the 125-shape shard takes 49 us either
+    // way, because every extra CTA costs ~5 us of slot time (TMA prologue + exact re-check) and the merge is one more launch
+    // (profiles/README.md).  It stays available for experiments (URED_NN_TAIL_SPLIT=1) and is off by default.
+    if (ns == 1 && env_int("URED_NN_TAIL_SPLIT", 0)) {
         int t = 1;
         while (t < 4 && t * 2 <= max_split) t *= 2;
         sh.nsplit = t;

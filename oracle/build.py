@@ -65,6 +65,49 @@ def build_ref(force=False):
     return ref_module_path()
 
 
+REF_EMD_SRC = "/root/reference/Density_aware_Chamfer_Distance/utils_v2/metrics/EMD"
+REF_EMD_NAME = "emd_ref"
+REF_EMD_DIR = os.path.join(REF_DIR, "emd")
+
+
+def ref_emd_module_path():
+    if not os.path.isdir(REF_EMD_DIR):
+        return None
+    for f in sorted(os.listdir(REF_EMD_DIR)):
+        if f.startswith(REF_EMD_NAME) and f.endswith(".so"):
+            return os.path.join(REF_EMD_DIR, f)
+    return None
+
+
+def build_ref_emd(force=False):
+    """Compile the reference's auction-EMD op (emd.cpp + emd_cuda.cu, as EMD/emd_module.py:31-36 JIT-loads them) for
+    sm_100a from its sources where they lie -> oracle/_ref/emd/emd_ref.so (the checker of the EMD re-rank)."""
+    if not os.path.isdir(REF_EMD_SRC):
+        return ref_emd_module_path()
+    if not force and ref_emd_module_path():
+        return ref_emd_module_path()
+    os.makedirs(REF_EMD_DIR, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    os.environ.setdefault("MAX_JOBS", "4")
+    from torch.utils.cpp_extension import load
+    load(name=REF_EMD_NAME,
+         sources=[os.path.join(REF_EMD_SRC, "emd.cpp"), os.path.join(REF_EMD_SRC, "emd_cuda.cu")],
+         build_directory=REF_EMD_DIR, verbose=False, is_python_module=True)
+    return ref_emd_module_path()
+
+
+def load_ref_emd():
+    path = ref_emd_module_path()
+    if path is None:
+        return None
+    import importlib.util
+    import torch  # noqa: F401
+    spec = importlib.util.spec_from_file_location(REF_EMD_NAME, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load_ref():
     """Import the prebuilt reference op (needs torch; callable only with a GPU)."""
     path = ref_module_path()

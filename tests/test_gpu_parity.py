@@ -623,3 +623,20 @@ def test_size_limits_at_the_boundary(ured, oracle):
     want1 = diff1.sum(0)
     want1.index_add_(0, i2.long().view(-1), (-diff2).view(-1, 3))
     assert torch.allclose(g1[0].double(), want1, rtol=1e-4, atol=1e-3)
+
+
+def test_tail_split_launch_plan_returns_the_same_bits(ured, monkeypatch):
+    """URED_NN_TAIL_SPLIT=1 cuts only the last partial wave of work items into candidate ranges (an experiment knob, off by
+    default because it does not pay): the merged result must be bit-identical to the unsplit launch."""
+    import ctypes
+    lib = ured._native.load()
+    B, n = 125, 2048
+    a, b = dev(make_clouds(210, B, n, "S")), dev(make_clouds(211, B, n, "S") * 0.97)
+    want = ured.nn_forward(a, b)
+    monkeypatch.setenv("URED_NN_TAIL_SPLIT", "1")
+    v, q, t, ns, items, split = (ctypes.c_int() for _ in range(6))
+    lib.ured_nn_launch_shape(B, n, n, 0, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns), ctypes.byref(items), ctypes.byref(split))
+    assert (items.value, split.value, ns.value) == (1000, 260, 4)
+    got = ured.nn_forward(a, b)
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
