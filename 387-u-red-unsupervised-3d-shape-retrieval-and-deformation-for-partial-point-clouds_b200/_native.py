@@ -45,6 +45,9 @@ _SIGNATURES = {
     "ured_dcd_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ured_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "ured_topk_smallest": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "ured_emd_workspace_bytes": (_sz, [_i, _i]),
+    "ured_emd_forward": (_i, [_p, _p, _i, _i, _f, _i, _p, _p, _p, _sz, _p]),
+    "ured_emd_backward": (_i, [_p, _p, _i, _i, _p, _p, _p, _p]),
     "ured_probe_ffma": (_i, [_p, _i, _i, ctypes.POINTER(ctypes.c_double), _p]),
     "ured_xchg_bytes": (_sz, [_i, _i, _i]),
     "ured_xchg_alloc": (_i, [_sz, ctypes.POINTER(ctypes.c_void_p)]),

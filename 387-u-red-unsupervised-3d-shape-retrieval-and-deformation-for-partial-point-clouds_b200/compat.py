@@ -9,8 +9,9 @@
     #   from pytorch3d.loss import chamfer_distance ; from pytorch3d.ops import knn_points (loss/chamfer_loss.py:1, loss/basic_loss.py)
     # resolve to this package.
 
-Only names on the Chamfer hot path are provided.  `emd` / `EMDLoss` / `calc_emd` (the auction EMD op, out of scope) are
-placeholders that raise when CALLED, so importing modules that merely mention them keeps working.
+`emd` / `calc_emd` resolve to the B200 auction-EMD kernel (emd_module.py).  `Shape_Measure.distance.EMDLoss` -- a module
+that is neither vendored nor pinned in the reference, with an unknown call contract -- stays a placeholder that raises
+when CALLED, so importing modules that merely mention it keeps working.
 
 `Density_aware_Chamfer_Distance.*` and `Shape_Measure.*` are ALWAYS aliased: they are exactly what this package
 replaces, and with the reference root on sys.path (the documented flow) the genuine DCD package is importable -- leaving
@@ -89,15 +90,18 @@ def _really_installed(name):
 
 def install(force=False):
     """Register the alias modules in sys.modules; returns the list of names installed."""
-    emd = _OutOfScope("emd")
+    from . import emd_module as _emd
+    emd = _emd.emdModule
     mods = {
         "Density_aware_Chamfer_Distance": {},
         "Density_aware_Chamfer_Distance.utils_v2": {},
         "Density_aware_Chamfer_Distance.utils_v2.metrics": dict(cd=chamfer_3DDist, fscore=_mu.fscore, emd=emd, __all__=["cd", "fscore", "emd"]),
         "Density_aware_Chamfer_Distance.utils_v2.metrics.CD": dict(cd=chamfer_3DDist, fscore=_mu.fscore),
+        "Density_aware_Chamfer_Distance.utils_v2.metrics.EMD": dict(emd=_emd.emdModule),
+        "Density_aware_Chamfer_Distance.utils_v2.metrics.EMD.emd_module": dict(emdFunction=_emd.emdFunction, emdModule=_emd.emdModule),
         "Density_aware_Chamfer_Distance.utils_v2.metrics.CD.chamfer3D": {},
         "Density_aware_Chamfer_Distance.utils_v2.metrics.CD.chamfer3D.dist_chamfer_3D": dict(chamfer_3DDist=chamfer_3DDist, chamfer_3DFunction=chamfer_3DFunction),
-        "Density_aware_Chamfer_Distance.utils_v2.model_utils": dict(calc_dcd=_mu.calc_dcd, calc_cd=_mu.calc_cd, calc_emd=_OutOfScope("calc_emd"),
+        "Density_aware_Chamfer_Distance.utils_v2.model_utils": dict(calc_dcd=_mu.calc_dcd, calc_cd=_mu.calc_cd, calc_emd=_emd.calc_emd,
                                                                    cd=chamfer_3DDist, fscore=_mu.fscore, emd=emd),
         "Shape_Measure": {},
         "Shape_Measure.distance": dict(ChamferLoss=ChamferLoss, EMDLoss=_OutOfScope("EMDLoss")),

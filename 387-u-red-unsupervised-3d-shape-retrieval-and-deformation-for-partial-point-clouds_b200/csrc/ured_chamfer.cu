@@ -33,6 +33,8 @@
 
 #include <atomic>
 
+#include <cooperative_groups.h>
+
 #include "ured_chamfer.h"
 
 namespace {
@@ -1400,6 +1402,219 @@ __global__ void __launch_bounds__(kXchgThreads) topk_exchange_kernel(const XchgP
 }
 
 // ------------------------------------------------------------------------------------------
+// EMD by the auction algorithm (the re-rank step after the Chamfer top-k: engine/generate_pair.py:101-104)
+// ------------------------------------------------------------------------------------------
+// Reference: DCD/utils_v2/metrics/EMD/emd_cuda.cu:23-316 -- per iteration seven kernel launches (count / prefix / list the
+// unassigned points, Bid, GetMax, Assign) over the whole batch, `iters` times from the host.  Here ONE launch runs the
+// whole auction: a thread-block cluster of 8 CTAs owns one pair of clouds, keeps the auction state in a small global
+// workspace (L2-resident) and separates the phases with cluster barriers (~0.2 us each) instead of kernel boundaries;
+// the bidders of an iteration are spread over all 8 x 512 threads, each group of threads scanning the candidate objects
+// from a shared-memory copy.  Arithmetic follows the reference instruction for instruction (value = 3.0 - sqrt(d2) -
+// price evaluated in double and rounded to float; best / second best with strict '>' in ascending index order), so the
+// assignment is the reference's whenever its own outcome is defined: when two bidders for one object are within its
+// 1e-6 tolerance the reference lets whichever thread stores last win (emd_cuda.cu:177-190) -- here the lowest point
+// index wins, one of the outcomes the reference itself can produce.
+namespace cg = cooperative_groups;
+constexpr int kEmdCluster = 8;
+constexpr int kEmdThreads = 512;
+constexpr int kEmdChunk = 4096;   // candidate objects staged in shared memory at a time (64 KB)
+
+struct EmdParams {
+    const float *xyz1, *xyz2;   // [B, n, 3]
+    float *dist;                // [B, n]
+    int *assignment;            // [B, n]
+    // workspace, per pair: price[n] | bid_inc[n] | assign_inv[n] | bid[n] | max_inc[n] (float bits) | max_idx[n] | unass[n] | cnt[16]
+    unsigned char *ws;
+    size_t ws_stride;
+    int n, iters;
+    float eps;
+};
+
+struct EmdBest { float best, better; int idx; };
+// combination of two partial scans: the larger value wins, the LOWER index on equal values; second best with multiplicity
+__device__ __forceinline__ EmdBest emd_combine(const EmdBest &a, const EmdBest &b) {
+    EmdBest r;
+    const bool take_b = b.best > a.best || (b.best == a.best && b.idx >= 0 && (a.idx < 0 || b.idx < a.idx));
+    const EmdBest &hi = take_b ? b : a, &lo = take_b ? a : b;
+    r.best = hi.best; r.idx = hi.idx;
+    r.better = fmaxf(fmaxf(hi.better, lo.best), lo.better);
+    return r;
+}
+
+__global__ void __cluster_dims__(kEmdCluster, 1, 1) __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdParams p) {
+    extern __shared__ float esm[];          // xyz2 chunk [3 * kEmdChunk] | price chunk [kEmdChunk]
+    __shared__ int s_scan[kEmdThreads / 32 + 1];
+    __shared__ int s_total;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const size_t pair = blockIdx.x / kEmdCluster;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.n;
+    const float *x1 = p.xyz1 + pair * n * 3, *x2 = p.xyz2 + pair * n * 3;
+    int *assignment = p.assignment + pair * n;
+    unsigned char *w = p.ws + pair * p.ws_stride;
+    float *price = reinterpret_cast<float *>(w);
+    float *bid_inc = price + n;
+    int *assign_inv = reinterpret_cast<int *>(bid_inc + n);
+    int *bid = assign_inv + n;
+    unsigned *max_inc = reinterpret_cast<unsigned *>(bid + n);
+    int *max_idx = reinterpret_cast<int *>(max_inc + n);
+    int *unass = max_idx + n;
+    int *cnt = unass + n;                   // cnt[rank] = unassigned points in this CTA's slice
+    const int gthreads = kEmdCluster * kEmdThreads, gtid = rank * kEmdThreads + tid;
+
+    // ---- initial state (emd_module.py:53-57: zeros, assignment = assignment_inv = -1) --------------------------------
+    for (int i = gtid; i < n; i += gthreads) {
+        price[i] = 0.0f; assignment[i] = -1; assign_inv[i] = -1; max_inc[i] = 0u; max_idx[i] = 0x7fffffff;
+    }
+    __threadfence();
+    cluster.sync();
+
+    const int slice = (n + kEmdCluster - 1) / kEmdCluster;   // this CTA lists the unassigned points of [lo, hi)
+    const int lo = min(n, rank * slice), hi = min(n, lo + slice);
+
+    for (int it = 0; it < p.iters; it++) {
+        const bool last = it == p.iters - 1;
+        // ---- 1. list the unassigned points, in ascending order (emd_cuda.cu:31-100 do it with a scan and atomics) ------
+        int base = 0;                        // running count of this CTA's slice
+        for (int i0 = lo; i0 < hi; i0 += kEmdThreads) {
+            const int i = i0 + tid;
+            const int un = (i < hi && __ldcg(&assignment[i]) == -1) ? 1 : 0;
+            const unsigned ballot = __ballot_sync(0xffffffffu, un);
+            if (lane == 0) s_scan[warp] = __popc(ballot);
+            __syncthreads();
+            if (warp == 0) {
+                int v = lane < kEmdThreads / 32 ? s_scan[lane] : 0, inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+                if (lane < kEmdThreads / 32) s_scan[lane] = inc - v;
+                if (lane == 31) s_total = inc;
+            }
+            __syncthreads();
+            // positions are relative to the slice for now; the slice's offset is added once all counts are known
+            if (un) unass[lo + base + s_scan[warp] + __popc(ballot & ((1u << lane) - 1u))] = i;
+            base += s_total;
+            __syncthreads();
+        }
+        if (tid == 0) cnt[rank] = base;
+        __threadfence();
+        cluster.sync();
+        int U = 0, my_off = 0;
+        for (int r = 0; r < kEmdCluster; r++) { const int c = __ldcg(&cnt[r]); if (r < rank) my_off += c; U += c; }
+        (void)my_off;
+        if (U == 0) break;                    // everything is assigned: the remaining iterations change nothing
+        // bidder g of the iteration = g-th unassigned point: slice r holds cnt[r] of them at unass[lo_r ...]
+        auto bidder = [&](int g) {
+            int r = 0, c;
+            while (g >= (c = __ldcg(&cnt[r]))) { g -= c; r++; }
+            return __ldcg(&unass[min(n, r * slice) + g]);
+        };
+
+        // ---- 2. Bid (emd_cuda.cu:103-175): tpb threads per bidder, each scanning a range of every candidate chunk --------
+        int tpb = 1;
+        while (tpb < 32 && (long long)U * tpb * 2 <= gthreads) tpb *= 2;
+        const int groups = gthreads / tpb;    // bidders in flight at a time
+        const int sub = gtid % tpb;
+        for (int g0 = 0; g0 < U; g0 += groups) {
+            const int g = g0 + gtid / tpb;
+            const bool active = g < U;
+            int j = -1;
+            float qx = 0.f, qy = 0.f, qz = 0.f;
+            if (active) { j = bidder(g); qx = x1[j * 3 + 0]; qy = x1[j * 3 + 1]; qz = x1[j * 3 + 2]; }
+            EmdBest acc; acc.best = -1e9f; acc.better = -1e9f; acc.idx = -1;
+            for (int k2 = 0; k2 < n; k2 += kEmdChunk) {
+                const int end_k = min(n, k2 + kEmdChunk) - k2;
+                __syncthreads();
+                for (int t = tid; t < end_k * 3; t += kEmdThreads) esm[t] = x2[(size_t)k2 * 3 + t];
+                for (int t = tid; t < end_k; t += kEmdThreads) esm[3 * kEmdChunk + t] = __ldcg(&price[k2 + t]);
+                __syncthreads();
+                if (active) {
+                    const int delta = (end_k + tpb - 1) / tpb;
+                    const int l = sub * delta, r = min((sub + 1) * delta, end_k);
+                    for (int k = l; k < r; k++) {
+                        const float dx = __fsub_rn(esm[k * 3 + 0], qx), dy = __fsub_rn(esm[k * 3 + 1], qy), dz = __fsub_rn(esm[k * 3 + 2], qz);
+                        const float s2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                        // "3.0 - sqrtf(..) - price" with a double literal: evaluated in double, rounded once to float
+                        const float d = (float)((3.0 - (double)sqrtf(s2)) - (double)esm[3 * kEmdChunk + k]);
+                        if (d > acc.best) { acc.better = acc.best; acc.best = d; acc.idx = k + k2; }
+                        else if (d > acc.better) acc.better = d;
+                    }
+                }
+            }
+            // combine the tpb partial scans of a bidder (a power of two within one warp)
+            for (int o = 1; o < tpb; o <<= 1) {
+                EmdBest oth;
+                oth.best = __shfl_xor_sync(0xffffffffu, acc.best, o);
+                oth.better = __shfl_xor_sync(0xffffffffu, acc.better, o);
+                oth.idx = __shfl_xor_sync(0xffffffffu, acc.idx, o);
+                acc = emd_combine(acc, oth);
+            }
+            if (active && sub == 0) {
+                const float inc = __fadd_rn(__fsub_rn(acc.best, acc.better), p.eps);
+                bid[j] = acc.idx;
+                bid_inc[j] = inc;
+                atomicMax(&max_inc[acc.idx], __float_as_uint(fmaxf(inc, 0.0f)));   // increments are >= 0: bit order == value order
+                max_idx[acc.idx] = 0x7fffffff;                                      // (reset for the arg-max of step 3)
+            }
+        }
+        __threadfence();
+        cluster.sync();
+        // ---- 3. GetMax (emd_cuda.cu:177-190): who placed the highest bid on each object (tolerance 1e-6, in double) ------
+        for (int g = gtid; g < U; g += gthreads) {
+            const int j = bidder(g);
+            const int b_id = __ldcg(&bid[j]);
+            const double inc = (double)__ldcg(&bid_inc[j]), mx = (double)__uint_as_float(__ldcg(&max_inc[b_id]));
+            if (inc - 1e-6 <= mx && mx <= inc + 1e-6) atomicMin(&max_idx[b_id], j);
+        }
+        __threadfence();
+        cluster.sync();
+        // ---- 4. Assign (emd_cuda.cu:192-212) -------------------------------------------------------------------------------
+        for (int g = gtid; g < U; g += gthreads) {
+            const int j = bidder(g);
+            const int b_id = __ldcg(&bid[j]);
+            if (last || __ldcg(&max_idx[b_id]) == j) {
+                const int prev = __ldcg(&assign_inv[b_id]);
+                if (!last && prev != -1) assignment[prev] = -1;
+                assign_inv[b_id] = j;
+                assignment[j] = b_id;
+                price[b_id] = __fadd_rn(__ldcg(&price[b_id]), __ldcg(&bid_inc[j]));
+                max_inc[b_id] = 0u;
+            }
+        }
+        __threadfence();
+        cluster.sync();
+    }
+    cluster.sync();
+    // ---- CalcDist (emd_cuda.cu:214-224) ------------------------------------------------------------------------------------
+    for (int j = gtid; j < n; j += gthreads) {
+        const int k = __ldcg(&assignment[j]);
+        float d = 0.0f;
+        if (k >= 0) {
+            const float dx = __fsub_rn(x1[j * 3 + 0], x2[k * 3 + 0]), dy = __fsub_rn(x1[j * 3 + 1], x2[k * 3 + 1]), dz = __fsub_rn(x1[j * 3 + 2], x2[k * 3 + 2]);
+            d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+        }
+        p.dist[pair * n + j] = d;
+    }
+}
+
+// emd_cuda.cu:279-300: grad_xyz1 = 2 g (x1 - x2[assignment]); xyz2 gets no gradient in the reference
+__global__ void __launch_bounds__(256) emd_grad_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                                                      const float *__restrict__ graddist, const int *__restrict__ assignment,
+                                                      float *__restrict__ gradxyz1, int n, size_t total) {
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= total) return;
+    const size_t b = t / n;
+    const int k = assignment[t];
+    const float g = __fmul_rn(graddist[t], 2.0f);
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (k >= 0) {
+        const float *a = xyz1 + t * 3, *o = xyz2 + (b * n + k) * 3;
+        gx = __fmul_rn(g, __fsub_rn(a[0], o[0])); gy = __fmul_rn(g, __fsub_rn(a[1], o[1])); gz = __fmul_rn(g, __fsub_rn(a[2], o[2]));
+    }
+    gradxyz1[t * 3 + 0] = gx; gradxyz1[t * 3 + 1] = gy; gradxyz1[t * 3 + 2] = gz;
+}
+
+// ------------------------------------------------------------------------------------------
 // FP32 FMA peak probe: the measured denominator of the roofline (MEASURED_PEAKS.json has no FP32 figure)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ffma_probe_kernel(float *sink, int iters, float a, float b) {
@@ -1749,6 +1964,42 @@ int ured_probe_ffma(float *sink, int blocks, int iters, double *flop, void *stre
     URED_COUNT_LAUNCH();
     if (flop) *flop = (double)blocks * 256.0 * (double)iters * 64.0 * 2.0;
     return check_cuda(cudaGetLastError(), "ffma_probe_kernel launch");
+}
+
+// ---- EMD (auction) -------------------------------------------------------------------------------------------------
+size_t ured_emd_workspace_bytes(int B, int n) {
+    if (B <= 0 || n <= 0) return 256;
+    return align_up((size_t)B * align_up((size_t)n * 7 * 4 + 64, 256), 256);
+}
+
+int ured_emd_forward(const float *xyz1, const float *xyz2, int B, int n, float eps, int iters, float *dist, int *assignment,
+                     void *workspace, size_t workspace_bytes, void *stream) {
+    if (B < 0 || n < 0 || iters < 0) return fail_arg(URED_E_SHAPE, "ured_emd_forward: negative size");
+    if (B == 0 || n == 0) return 0;
+    if (!xyz1 || !xyz2 || !dist || !assignment || !workspace) return fail_arg(URED_E_NULL, "ured_emd_forward: NULL pointer");
+    if ((uintptr_t)workspace % 256 || workspace_bytes < ured_emd_workspace_bytes(B, n)) return fail_arg(URED_E_WORKSPACE, "ured_emd_forward: workspace too small or misaligned");
+    if ((long long)B * kEmdCluster > 0x7fffffffll) return fail_arg(URED_E_SHAPE, "ured_emd_forward: too many pairs");
+    EmdParams p;
+    p.xyz1 = xyz1; p.xyz2 = xyz2; p.dist = dist; p.assignment = assignment;
+    p.ws = (unsigned char *)workspace; p.ws_stride = align_up((size_t)n * 7 * 4 + 64, 256);
+    p.n = n; p.iters = iters; p.eps = eps;
+    const size_t smem = (size_t)4 * (n < kEmdChunk ? n : kEmdChunk) * sizeof(float);
+    if (smem > kSmemOptIn)
+        URED_CUDA(cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kEmdChunk * (int)sizeof(float)), "emd smem attribute");
+    emd_auction_kernel<<<(unsigned)(B * kEmdCluster), kEmdThreads, smem, (cudaStream_t)stream>>>(p);
+    URED_COUNT_LAUNCH();
+    return check_cuda(cudaGetLastError(), "emd_auction_kernel launch");
+}
+
+int ured_emd_backward(const float *xyz1, const float *xyz2, int B, int n, const float *graddist, const int *assignment,
+                      float *gradxyz1, void *stream) {
+    if (B < 0 || n < 0) return fail_arg(URED_E_SHAPE, "ured_emd_backward: negative size");
+    if (B == 0 || n == 0) return 0;
+    if (!xyz1 || !xyz2 || !graddist || !assignment || !gradxyz1) return fail_arg(URED_E_NULL, "ured_emd_backward: NULL pointer");
+    const size_t total = (size_t)B * n;
+    emd_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(xyz1, xyz2, graddist, assignment, gradxyz1, n, total);
+    URED_COUNT_LAUNCH();
+    return check_cuda(cudaGetLastError(), "emd_grad_kernel launch");
 }
 
 // ---- peer exchange (sharded retrieval) -----------------------------------------------------------------------------

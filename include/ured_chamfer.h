@@ -197,6 +197,25 @@ int ured_topk_smallest(const float *scores, int rows, int cols, int k, int idx_o
 int ured_merge_topk(const float *scores, const int *ids, int rows, int cols, int k,
                     float *out_scores, int *out_ids, void *stream);
 
+/* ---- EMD by the auction algorithm (re-rank of the Chamfer top-k) ---------------------------------------------------
+ * Replaces the pybind module `emd` of the reference: emd.forward / emd.backward
+ *     DCD/utils_v2/metrics/EMD/emd.cpp:13-30 -> emd_cuda.cu:226-316 (seven kernels per iteration, iterated from the host);
+ * Python surface emdFunction / emdModule (EMD/emd_module.py:39-91) and calc_emd (utils_v2/model_utils.py:72-77).
+ * xyz1 (prediction) and xyz2 (ground truth) are [B, n, 3] clouds of EQUAL size, coordinates expected in [0, 1] as in the
+ * reference (its value "3.0 - distance - price" assumes it).  dist [B, n] receives the squared distance of every xyz1 point
+ * to its assigned xyz2 point, assignment [B, n] that point's index (not necessarily a bijection, exactly as in the
+ * reference: the last iteration assigns every remaining bidder to the object it bid on).  One launch runs the whole
+ * auction: a cluster of 8 CTAs per pair, phases separated by cluster barriers.  Results equal the reference's whenever the
+ * reference's own outcome is defined; when two bidders for one object are within its 1e-6 tolerance the reference lets the
+ * last store win, this library the lowest point index.  No restriction on n (the reference needs n % 1024 == 0) or B (<= 512 there).
+ * workspace: ured_emd_workspace_bytes(B, n) bytes, 256-byte aligned.  ured_emd_backward fills gradxyz1 [B, n, 3]
+ * (the reference gives xyz2 no gradient: emd_module.py:81-84). */
+size_t ured_emd_workspace_bytes(int B, int n);
+int ured_emd_forward(const float *xyz1, const float *xyz2, int B, int n, float eps, int iters,
+                     float *dist, int *assignment, void *workspace, size_t workspace_bytes, void *stream);
+int ured_emd_backward(const float *xyz1, const float *xyz2, int B, int n,
+                      const float *graddist, const int *assignment, float *gradxyz1, void *stream);
+
 /* ---- measurement aid ------------------------------------------------------------------------------------------------
  * Launches a pure FFMA stream (8 independent chains per thread, blocks x 256 threads, 64 FFMA per iteration) and
  * reports its FLOP count; bench.py times it with CUDA events to obtain the FP32 FMA peak of the device it runs on. */

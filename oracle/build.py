@@ -28,6 +28,18 @@ def build_oracle(force=False):
     return ORACLE_SO
 
 
+EMD_SO = os.path.join(HERE, "liboracle_emd.so")
+
+
+def build_emd_oracle(force=False):
+    """gcc oracle/emd_oracle.c -> oracle/liboracle_emd.so (CPU restatement of the reference's auction EMD)."""
+    src = os.path.join(HERE, "emd_oracle.c")
+    if not force and os.path.exists(EMD_SO) and os.path.getmtime(EMD_SO) >= os.path.getmtime(src):
+        return EMD_SO
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", EMD_SO, src, "-lm"], check=True)
+    return EMD_SO
+
+
 SCREEN_SO = os.path.join(HERE, "libscreen_model.so")
 
 

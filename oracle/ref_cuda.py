@@ -48,3 +48,25 @@ def calc_dcd_fwd_bwd(ref, x, gt, alpha=1000, n_lambda=1):
     gx1, gx2 = torch.zeros_like(gt), torch.zeros_like(x)
     ref.backward(gt, x, gx1, gx2, g1.contiguous(), g2.contiguous(), i1, i2)
     return loss
+
+
+# ---- the reference's auction-EMD op (oracle/_ref/emd, built by oracle/build.py::build_ref_emd) ---------------------------
+def load_emd():
+    return build.load_ref_emd()
+
+
+def emd_forward(ref_emd, xyz1, xyz2, eps, iters):
+    """emd_module.py:41-68 around emd.forward: the reference's own buffer set-up, then its op.  n must be a multiple of 1024."""
+    B, n, _ = xyz1.shape
+    dev = xyz1.device
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, device=dev, dtype=dt)  # noqa: E731
+    dist = z(B, n)
+    assignment = z(B, n, dt=torch.int32) - 1
+    assignment_inv = z(B, n, dt=torch.int32) - 1
+    price, bid, bid_increments, max_increments = z(B, n), z(B, n, dt=torch.int32), z(B, n), z(B, n)
+    unass_idx, max_idx = z(B * n, dt=torch.int32), z(B * n, dt=torch.int32)
+    unass_cnt, unass_cnt_sum, cnt_tmp = z(512, dt=torch.int32), z(512, dt=torch.int32), z(512, dt=torch.int32)
+    ref_emd.forward(xyz1.contiguous(), xyz2.contiguous(), dist, assignment, price, assignment_inv, bid, bid_increments, max_increments,
+                    unass_idx, unass_cnt, unass_cnt_sum, cnt_tmp, max_idx, eps, iters)
+    torch.cuda.synchronize()
+    return dist, assignment
