@@ -1462,6 +1462,7 @@ __global__ void __cluster_dims__(kEmdCluster, 1, 1) __launch_bounds__(kEmdThread
     int *unass = max_idx + n;
     int *cnt = unass + n;                   // cnt[rank] = unassigned points in this CTA's slice
     const int gthreads = kEmdCluster * kEmdThreads, gtid = rank * kEmdThreads + tid;
+    float *sprice = esm + 3 * min(n, kEmdChunk);   // the launch sizes shared memory for min(n, kEmdChunk) candidates
 
     // ---- initial state (emd_module.py:53-57: zeros, assignment = assignment_inv = -1) --------------------------------
     for (int i = gtid; i < n; i += gthreads) {
@@ -1526,16 +1527,17 @@ __global__ void __cluster_dims__(kEmdCluster, 1, 1) __launch_bounds__(kEmdThread
                 const int end_k = min(n, k2 + kEmdChunk) - k2;
                 __syncthreads();
                 for (int t = tid; t < end_k * 3; t += kEmdThreads) esm[t] = x2[(size_t)k2 * 3 + t];
-                for (int t = tid; t < end_k; t += kEmdThreads) esm[3 * kEmdChunk + t] = __ldcg(&price[k2 + t]);
+                for (int t = tid; t < end_k; t += kEmdThreads) sprice[t] = __ldcg(&price[k2 + t]);
                 __syncthreads();
                 if (active) {
                     const int delta = (end_k + tpb - 1) / tpb;
                     const int l = sub * delta, r = min((sub + 1) * delta, end_k);
                     for (int k = l; k < r; k++) {
                         const float dx = __fsub_rn(esm[k * 3 + 0], qx), dy = __fsub_rn(esm[k * 3 + 1], qy), dz = __fsub_rn(esm[k * 3 + 2], qz);
-                        const float s2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                        // x2*x2 + y2*y2 + z2*z2 as nvcc contracts it (SASS of the reference build): fma(z,z, fma(x,x, y*y))
+                        const float s2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
                         // "3.0 - sqrtf(..) - price" with a double literal: evaluated in double, rounded once to float
-                        const float d = (float)((3.0 - (double)sqrtf(s2)) - (double)esm[3 * kEmdChunk + k]);
+                        const float d = (float)((3.0 - (double)sqrtf(s2)) - (double)sprice[k]);
                         if (d > acc.best) { acc.better = acc.best; acc.best = d; acc.idx = k + k2; }
                         else if (d > acc.better) acc.better = d;
                     }
@@ -1591,7 +1593,7 @@ __global__ void __cluster_dims__(kEmdCluster, 1, 1) __launch_bounds__(kEmdThread
         float d = 0.0f;
         if (k >= 0) {
             const float dx = __fsub_rn(x1[j * 3 + 0], x2[k * 3 + 0]), dy = __fsub_rn(x1[j * 3 + 1], x2[k * 3 + 1]), dz = __fsub_rn(x1[j * 3 + 2], x2[k * 3 + 2]);
-            d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+            d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));   // same contraction (checked against the reference op's bits)
         }
         p.dist[pair * n + j] = d;
     }

@@ -9,7 +9,8 @@
  *                       iteration every remaining bidder is assigned to the object it bid on
  *   CalcDist :214-224   dist = |x1 - x2[assignment]|^2
  * and the host loop :256-267 (iters iterations).  Arithmetic is written with explicit fmaf in the contraction nvcc 12.9
- * emits for sm_100a (checked in the SASS of the compiled reference): d2 = fma(dz,dz, fma(dy,dy, dx*dx)).
+ * emits for sm_100a (checked in the SASS of the compiled reference and against its output bits): a*a + b*b + c*c becomes
+ * fma(c,c, fma(a,a, b*b)), i.e. d2 = fma(dz,dz, fma(dx,dx, dy*dy)).
  * Build with -ffp-contract=off.
  *
  * Where the reference is racy -- several bidders within the 1e-6 tolerance: its last store wins -- this oracle takes
@@ -43,7 +44,7 @@ int emd_oracle_forward(const float *xyz1, const float *xyz2, int B, int n, float
                 const float x1 = p1[j * 3 + 0], y1 = p1[j * 3 + 1], z1 = p1[j * 3 + 2];
                 for (int k = 0; k < n; k++) {
                     const float x2 = p2[k * 3 + 0] - x1, y2 = p2[k * 3 + 1] - y1, z2 = p2[k * 3 + 2] - z1;
-                    const float s2 = fmaf(z2, z2, fmaf(y2, y2, x2 * x2));
+                    const float s2 = fmaf(z2, z2, fmaf(x2, x2, y2 * y2));
                     const float d = (float)((3.0 - (double)sqrtf(s2)) - (double)price[k]);
                     if (d > best) { better = best; best = d; best_i = k; }
                     else if (d > better) better = d;
@@ -80,7 +81,7 @@ int emd_oracle_forward(const float *xyz1, const float *xyz2, int B, int n, float
             float d = 0.0f;
             if (k >= 0) {
                 const float dx = p1[j * 3 + 0] - p2[k * 3 + 0], dy = p1[j * 3 + 1] - p2[k * 3 + 1], dz = p1[j * 3 + 2] - p2[k * 3 + 2];
-                d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                d = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
             }
             dist[(size_t)b * n + j] = d;
         }
