@@ -448,6 +448,33 @@ def reference_cuda_leg(ctx, x_dev, gt_dev, pairs_per_step, ours_ms):
         return {"unavailable": f"{type(exc).__name__}: {exc}"}
 
 
+def emd_rerank_leg(ctx):
+    """The re-rank step after the Chamfer top-k (engine/generate_pair.py:95-104): EMD of one target against its 20 best
+    candidates, 2048 points, eps 0.005, 50 auction iterations -- our cluster kernel (one launch) next to the reference's own
+    op (oracle/_ref/emd: seven launches per iteration), same inputs.  A sub-record, not part of the headline metric."""
+    torch, ured, dev = ctx.torch, ctx.ured, ctx.dev
+    k, n, eps, iters = 20, 2048, 0.005, 50
+    g = torch.Generator().manual_seed(321)
+    tgt = torch.rand(1, n, 3, generator=g).to(dev).repeat(k, 1, 1).contiguous()
+    cands = torch.rand(k, n, 3, generator=g).to(dev)
+    mod = ured.emdModule()
+    ms, _ = ctx.timed(lambda: mod(tgt, cands, eps, iters), 10, 3, collective=False)
+    rec = {"what": "EMD (auction) of 1 target vs its top-20 candidates, 2048 pts, eps 0.005, 50 iterations", "ms": ms,
+           "kernel": "emd_auction_kernel: one launch, a cluster of 8 CTAs per pair, phases separated by cluster barriers"}
+    try:
+        from oracle import ref_cuda
+        ref = ref_cuda.load_emd()
+        if ref is not None:
+            ms_ref, _ = ctx.timed(lambda: ref_cuda.emd_forward(ref, tgt, cands, eps, iters), 5, 2, collective=False)
+            d_ref, a_ref = ref_cuda.emd_forward(ref, tgt, cands, eps, iters)
+            d_our, a_our = mod(tgt, cands, eps, iters)
+            rec["reference_op"] = {"ms": ms_ref, "speedup": ms_ref / ms, "pairs_with_identical_assignment": int((a_ref == a_our).all(1).sum()),
+                                   "pairs": k, "what": "unmodified emd.cpp/emd_cuda.cu built for sm_100a (oracle/_ref/emd), incl. its buffer set-up as in emd_module.py"}
+    except Exception as exc:
+        rec["reference_op"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+    return rec
+
+
 # ------------------------------------------------------------------------------------------------
 # the Chamfer+DCD fwd+bwd workloads (cfg2 headline; cfg1 / cfg4 as sub-records)
 # ------------------------------------------------------------------------------------------------
@@ -617,6 +644,7 @@ def main():
                 torch.cuda.empty_cache()
             line["configs"] = subs
             line["reference_cuda_op"] = reference_cuda_leg(ctx, x_dev, gt_dev, main_rec["pairs_per_step"], main_rec["ms_per_step"])
+            line["emd_rerank"] = emd_rerank_leg(ctx)
         del x_dev, gt_dev
         torch.cuda.empty_cache()
         retr = {}

@@ -77,7 +77,7 @@ def test_calc_emd_backward_and_rerank(ured, emd_oracle):
     for q in range(2):
         for c in range(4):
             e, _ = ured.calc_emd(tg[q:q + 1], lib[ids_sorted[q, c].long()].unsqueeze(0))
-            assert torch.equal(e[0], emd_sorted[q, c])
+            assert torch.allclose(e[0], emd_sorted[q, c], rtol=1e-6)   # (torch reduces a 1-row and an 8-row batch in different orders)
 
 
 def test_emd_argument_errors(ured):
