@@ -1441,10 +1441,11 @@ __device__ __forceinline__ EmdBest emd_combine(const EmdBest &a, const EmdBest &
     return r;
 }
 
-__global__ void __cluster_dims__(kEmdCluster, 1, 1) __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdParams p) {
+__global__ void __cluster_dims__(kEmdCluster, 1, 1) __launch_bounds__(kEmdThreads, 2) emd_auction_kernel(const EmdParams p) {
     extern __shared__ float esm[];          // xyz2 chunk [3 * kEmdChunk] | price chunk [kEmdChunk]
     __shared__ int s_scan[kEmdThreads / 32 + 1];
     __shared__ int s_total;
+    __shared__ int s_cnt[kEmdCluster + 1];   // exclusive prefix of the slices' unassigned counts (this iteration)
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const size_t pair = blockIdx.x / kEmdCluster;
@@ -1468,9 +1469,9 @@ __global__ void __cluster_dims__(kEmdCluster, 1, 1) __launch_bounds__(kEmdThread
     for (int i = gtid; i < n; i += gthreads) {
         price[i] = 0.0f; assignment[i] = -1; assign_inv[i] = -1; max_inc[i] = 0u; max_idx[i] = 0x7fffffff;
     }
-    __threadfence();
     cluster.sync();
 
+    bool x2_resident = false;
     const int slice = (n + kEmdCluster - 1) / kEmdCluster;   // this CTA lists the unassigned points of [lo, hi)
     const int lo = min(n, rank * slice), hi = min(n, lo + slice);
 
@@ -1498,17 +1499,21 @@ __global__ void __cluster_dims__(kEmdCluster, 1, 1) __launch_bounds__(kEmdThread
             __syncthreads();
         }
         if (tid == 0) cnt[rank] = base;
-        __threadfence();
-        cluster.sync();
-        int U = 0, my_off = 0;
-        for (int r = 0; r < kEmdCluster; r++) { const int c = __ldcg(&cnt[r]); if (r < rank) my_off += c; U += c; }
-        (void)my_off;
+        cluster.sync();   // (arrive.release / wait.acquire at cluster scope: orders the global-memory state between the phases)
+        if (tid == 0) {
+            int run = 0;
+            for (int r = 0; r < kEmdCluster; r++) { s_cnt[r] = run; run += __ldcg(&cnt[r]); }
+            s_cnt[kEmdCluster] = run;
+        }
+        __syncthreads();
+        const int U = s_cnt[kEmdCluster];
         if (U == 0) break;                    // everything is assigned: the remaining iterations change nothing
-        // bidder g of the iteration = g-th unassigned point: slice r holds cnt[r] of them at unass[lo_r ...]
+        // bidder g of the iteration = g-th unassigned point: slice r holds its unassigned points at unass[lo_r ...]
         auto bidder = [&](int g) {
-            int r = 0, c;
-            while (g >= (c = __ldcg(&cnt[r]))) { g -= c; r++; }
-            return __ldcg(&unass[min(n, r * slice) + g]);
+            int r = 0;
+#pragma unroll
+            for (int q = 1; q < kEmdCluster; q++) r += g >= s_cnt[q] ? 1 : 0;
+            return __ldcg(&unass[min(n, r * slice) + (g - s_cnt[r])]);
         };
 
         // ---- 2. Bid (emd_cuda.cu:103-175): tpb threads per bidder, each scanning a range of every candidate chunk --------
@@ -1526,20 +1531,42 @@ __global__ void __cluster_dims__(kEmdCluster, 1, 1) __launch_bounds__(kEmdThread
             for (int k2 = 0; k2 < n; k2 += kEmdChunk) {
                 const int end_k = min(n, k2 + kEmdChunk) - k2;
                 __syncthreads();
-                for (int t = tid; t < end_k * 3; t += kEmdThreads) esm[t] = x2[(size_t)k2 * 3 + t];
+                if (n > kEmdChunk || !x2_resident)   // a cloud that fits one chunk is staged once for the whole auction; prices change every iteration
+                    for (int t = tid; t < end_k * 3; t += kEmdThreads) esm[t] = x2[(size_t)k2 * 3 + t];
+                x2_resident = true;
                 for (int t = tid; t < end_k; t += kEmdThreads) sprice[t] = __ldcg(&price[k2 + t]);
                 __syncthreads();
                 if (active) {
-                    const int delta = (end_k + tpb - 1) / tpb;
-                    const int l = sub * delta, r = min((sub + 1) * delta, end_k);
-                    for (int k = l; k < r; k++) {
+                    // Sub-thread `sub` takes candidates sub, sub + tpb, ...: the lanes of a warp then read consecutive candidates
+                    // (conflict-free; contiguous per-thread ranges of 2^m candidates would put all lanes on ONE bank).  The
+                    // interleaving is invisible in the result: emd_combine breaks equal values by the lower index.
+                    // The reference evaluates "3.0 - sqrtf(d2) - price" in DOUBLE (the literal is a double) and rounds to float;
+                    // FP64 adds and conversions are the slow instructions of this loop on B200.  Screen in float first: the float
+                    // value differs from the reference's by < 4e-7 * max(4, |v|), so a candidate more than `margin` below the
+                    // range's second-best float value can be neither the best nor the second best -- only the few candidates
+                    // above that threshold are re-evaluated the reference's way (x2*x2 + y2*y2 + z2*z2 as nvcc contracts it:
+                    // fma(z,z, fma(x,x, y*y)); checked against the reference op's bits).
+                    auto approx = [&](int k, float &s2) {
                         const float dx = __fsub_rn(esm[k * 3 + 0], qx), dy = __fsub_rn(esm[k * 3 + 1], qy), dz = __fsub_rn(esm[k * 3 + 2], qz);
-                        // x2*x2 + y2*y2 + z2*z2 as nvcc contracts it (SASS of the reference build): fma(z,z, fma(x,x, y*y))
-                        const float s2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-                        // "3.0 - sqrtf(..) - price" with a double literal: evaluated in double, rounded once to float
-                        const float d = (float)((3.0 - (double)sqrtf(s2)) - (double)sprice[k]);
-                        if (d > acc.best) { acc.better = acc.best; acc.best = d; acc.idx = k + k2; }
-                        else if (d > acc.better) acc.better = d;
+                        s2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                        return __fsub_rn(__fsub_rn(3.0f, sqrtf(s2)), sprice[k]);
+                    };
+                    float t1 = -kInf, t2 = -kInf, s2;
+#pragma unroll 4
+                    for (int k = sub; k < end_k; k += tpb) {
+                        const float v = approx(k, s2);
+                        t2 = fmaxf(t2, fminf(t1, v));
+                        t1 = fmaxf(t1, v);
+                    }
+                    const float thr = t2 - 1.9073486e-6f /* 2^-19 */ * fmaxf(4.0f, fabsf(t2));   // (-inf when the range holds < 2 candidates)
+#pragma unroll 4
+                    for (int k = sub; k < end_k; k += tpb) {
+                        const float v = approx(k, s2);
+                        if (v >= thr) {
+                            const float d = (float)((3.0 - (double)sqrtf(s2)) - (double)sprice[k]);
+                            if (d > acc.best) { acc.better = acc.best; acc.best = d; acc.idx = k + k2; }
+                            else if (d > acc.better) acc.better = d;
+                        }
                     }
                 }
             }
@@ -1559,8 +1586,7 @@ __global__ void __cluster_dims__(kEmdCluster, 1, 1) __launch_bounds__(kEmdThread
                 max_idx[acc.idx] = 0x7fffffff;                                      // (reset for the arg-max of step 3)
             }
         }
-        __threadfence();
-        cluster.sync();
+        cluster.sync();   // (arrive.release / wait.acquire at cluster scope: orders the global-memory state between the phases)
         // ---- 3. GetMax (emd_cuda.cu:177-190): who placed the highest bid on each object (tolerance 1e-6, in double) ------
         for (int g = gtid; g < U; g += gthreads) {
             const int j = bidder(g);
@@ -1568,8 +1594,7 @@ __global__ void __cluster_dims__(kEmdCluster, 1, 1) __launch_bounds__(kEmdThread
             const double inc = (double)__ldcg(&bid_inc[j]), mx = (double)__uint_as_float(__ldcg(&max_inc[b_id]));
             if (inc - 1e-6 <= mx && mx <= inc + 1e-6) atomicMin(&max_idx[b_id], j);
         }
-        __threadfence();
-        cluster.sync();
+        cluster.sync();   // (arrive.release / wait.acquire at cluster scope: orders the global-memory state between the phases)
         // ---- 4. Assign (emd_cuda.cu:192-212) -------------------------------------------------------------------------------
         for (int g = gtid; g < U; g += gthreads) {
             const int j = bidder(g);
@@ -1583,8 +1608,7 @@ __global__ void __cluster_dims__(kEmdCluster, 1, 1) __launch_bounds__(kEmdThread
                 max_inc[b_id] = 0u;
             }
         }
-        __threadfence();
-        cluster.sync();
+        cluster.sync();   // (arrive.release / wait.acquire at cluster scope: orders the global-memory state between the phases)
     }
     cluster.sync();
     // ---- CalcDist (emd_cuda.cu:214-224) ------------------------------------------------------------------------------------
