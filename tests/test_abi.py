@@ -50,6 +50,20 @@ def test_argument_errors_do_not_need_a_device(ured):
     # empty batches are a successful no-op
     assert lib.ured_chamfer_forward(None, None, 0, 8, 8, None, None, None, None, None, None, None, 0, 0, None) == 0
     assert lib.ured_topk_smallest(None, 0, 5, 2, 0, None, None, None) == 0
+    # round-2 entry points: the peer exchange and the auction EMD
+    assert lib.ured_xchg_bytes(8, 64, 10) > 0 and lib.ured_xchg_bytes(8, 64, 10) % 256 == 0
+    assert lib.ured_xchg_bytes(17, 1, 10) == 0 and lib.ured_xchg_bytes(8, 513, 10) == 0 and lib.ured_xchg_bytes(8, 1, 65) == 0 and lib.ured_xchg_bytes(0, 1, 1) == 0
+    assert lib.ured_topk_exchange(None, 4, 20, 10, 0, None, 2, 0, 4, None, None, 100, None) == E_NULL
+    assert lib.ured_topk_exchange(None, 4, 20, 10, 0, None, 17, 0, 4, None, None, 100, None) == E_RANGE     # world <= 16
+    assert lib.ured_topk_exchange(None, 4, 20, 65, 0, None, 2, 0, 4, None, None, 100, None) == E_RANGE      # k <= 64
+    assert lib.ured_topk_exchange(None, 0, 20, 10, 0, None, 2, 0, 0, None, None, 100, None) == 0           # no query rows: nothing to do
+    assert lib.ured_emd_workspace_bytes(20, 2048) >= 20 * 2048 * 7 * 4 and lib.ured_emd_workspace_bytes(20, 2048) % 256 == 0
+    assert lib.ured_emd_forward(None, None, 2, 64, 0.005, 10, None, None, None, 0, None) == E_NULL
+    assert lib.ured_emd_forward(None, None, -2, 64, 0.005, 10, None, None, None, 0, None) == E_SHAPE
+    assert lib.ured_emd_forward(None, None, 0, 64, 0.005, 10, None, None, None, 0, None) == 0
+    assert lib.ured_emd_backward(None, None, 2, 64, None, None, None, None) == E_NULL
+    assert lib.ured_nn_backward_one_direction(None, None, 2, 8, 8, None, None, None, None, None, None) == E_NULL
+    assert lib.ured_probe_ffma(None, 1, 1, None, None) == E_SHAPE
 
 
 def test_no_cpu_fallback(ured):
