@@ -114,3 +114,44 @@ def test_rankings_10k_library(ured, oracle, ref_op):
     assert torch.equal(sc.view(-1), ref[2])
     assert torch.equal(ured.topk_smallest(sc, k)[1].view(-1), want_sorted[:k])
     assert torch.equal(ured.topk_smallest(sc, 1024)[1].view(-1), want_sorted[:1024])
+
+
+def test_fused_fscore_matches_the_reference_function(ured):
+    """metrics/CD/fscore.py:3-16 inside the epilogue kernel (fscore_fused, calc_cd(calc_f1=True)) == the four torch ops, bit for bit:
+    the counts are exact in any order and the factor is torch's."""
+    g = torch.Generator().manual_seed(12)
+    for B, n1, n2, thr in [(16, 2048, 2048, 1e-4), (37, 2000, 1000, 1e-3), (3, 300, 500, 1e-4)]:
+        d1 = (torch.rand(B, n1, generator=g) ** 6 * 0.01).cuda()
+        d2 = (torch.rand(B, n2, generator=g) ** 6 * 0.01).cuda()
+        f, p1, p2 = ured.fscore_fused(d1, d2, thr)
+        wf, wp1, wp2 = ured.fscore(d1, d2, thr)
+        assert torch.equal(p1, wp1) and torch.equal(p2, wp2) and torch.equal(f, wf)
+    d1[0] = 1.0; d2[0] = 1.0                      # no point under the threshold: 0/0 is reported as 0 (fscore.py:15)
+    f, _, _ = ured.fscore_fused(d1, d2, 1e-4)
+    assert f[0].item() == 0.0
+    x, gt = make_clouds(5, 4, 1024, "S").cuda(), (make_clouds(6, 4, 1024, "S") * 0.99).cuda()
+    cd_p, cd_t, f1 = ured.calc_cd(x, gt, calc_f1=True)
+    dist1, dist2, _, _ = ured.chamfer_3DDist()(gt, x)
+    assert torch.equal(f1, ured.fscore(dist1, dist2)[0])
+
+
+def test_engine_metric_selection_and_exact_ranking(ured, oracle, ref_op):
+    """score_library(metrics=...) returns only what was asked for (cd_t alone skips the DCD histograms) with unchanged bits; the
+    engine in exact_ranking mode (the reference's torch reductions) returns the same ids as the fused default."""
+    S, n, k = 300, 2048, 10
+    lib_x = make_clouds(400, S, n, "S").cuda()
+    tg = make_clouds(401, 2, n, "S").cuda()
+    full = ured.score_library(tg, lib_x)
+    only = ured.score_library(tg, lib_x, metrics=("cd_t",))
+    assert set(only) == {"cd_t"} and torch.equal(only["cd_t"], full["cd_t"])
+    two = ured.score_library(tg, lib_x, metrics=("dcd", "cd_p"))
+    assert set(two) == {"dcd", "cd_p"} and torch.equal(two["dcd"], full["dcd"]) and torch.equal(two["cd_p"], full["cd_p"])
+    fused = ured.RetrievalEngine(lib_x, 0, 2, k=k).query(tg)
+    exact = ured.RetrievalEngine(lib_x, 0, 2, k=k, exact_ranking=True, use_graph=False).query(tg)
+    assert torch.equal(fused[1], exact[1]) and torch.equal(fused[0], exact[0])
+    # results survive the next query (the graph's static outputs are cloned)
+    again = ured.RetrievalEngine(lib_x, 0, 2, k=k)
+    first = again.query(tg)
+    keep = (first[0].clone(), first[1].clone())
+    again.query(make_clouds(402, 2, n, "S").cuda())
+    assert torch.equal(first[0], keep[0]) and torch.equal(first[1], keep[1])
