@@ -16,8 +16,14 @@
  *       .../chamfer_cuda.cpp:22-26,32 -> chamfer3D.cu:155-195
  *   torch-op body of calc_cd / calc_dcd                              ured_dcd_forward,
  *       DCD/utils_v2/model_utils.py:13-51, 53-70                     ured_dcd_backward
- *   torch.topk(cd_m, k, largest=False) ranking                       ured_topk_smallest
- *       dataset/dataset_utils.py:1043-1051
+ *   torch.topk(cd_m, k, largest=False) ranking                       ured_topk_smallest, ured_merge_topk,
+ *       dataset/dataset_utils.py:1043-1051                           ured_topk_exchange (sharded over GPUs)
+ *   fscore(dist1, dist2, threshold)                                  ured_dcd_forward_ex (fscore output)
+ *       DCD/utils_v2/metrics/CD/fscore.py:3-16
+ *   pytorch3d knn_points(K=1) of residual_retrieval_loss              ured_nn_packed(URED_FLAG_ONE_DIRECTION),
+ *       loss/basic_loss.py:249-265                                   ured_nn_backward_one_direction
+ *   emd.forward / emd.backward (auction EMD)                         ured_emd_forward, ured_emd_backward
+ *       DCD/utils_v2/metrics/EMD/emd.cpp:13-30 -> emd_cuda.cu:226-316
  *
  * Conventions (all entry points)
  *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
