@@ -19,7 +19,7 @@ from . import retrieval
 from . import compat
 from .graphed import GraphedDCD
 from .knn import knn1_points, residual_retrieval_loss
-from .retrieval import (RetrievalEngine, PackedClouds, score_all_pairs, write_pair_pickles, score_candidates, score_library, topk_smallest, retrieve,
+from .retrieval import (RetrievalEngine, PendingResult, PackedClouds, score_all_pairs, write_pair_pickles, score_candidates, score_library, topk_smallest, retrieve,
                         retrieve_sharded, shard_bounds, merge_topk, gather_and_merge)
 from .exchange import PeerExchange
 from .emd_module import emdFunction, emdModule, calc_emd, rerank_emd
@@ -27,7 +27,7 @@ from .emd_module import emdFunction, emdModule, calc_emd, rerank_emd
 __all__ = [
     "chamfer_3DDist", "chamfer_3DFunction", "nn_forward", "nn_backward", "check_finite", "cd", "fscore", "calc_cd", "calc_dcd", "chamfer_ragged",
     "ChamferLoss", "chamfer_distance2", "compute_cm_loss",
-    "knn1_points", "residual_retrieval_loss", "PackedClouds", "RetrievalEngine", "GraphedDCD", "score_candidates", "score_library", "score_all_pairs", "write_pair_pickles", "topk_smallest", "retrieve",
+    "knn1_points", "residual_retrieval_loss", "PackedClouds", "RetrievalEngine", "PendingResult", "GraphedDCD", "score_candidates", "score_library", "score_all_pairs", "write_pair_pickles", "topk_smallest", "retrieve",
     "retrieve_sharded", "shard_bounds", "merge_topk", "gather_and_merge", "PeerExchange", "fscore_fused", "torch_epilogue", "emdFunction", "emdModule", "calc_emd", "rerank_emd",
     "NativeLibraryError", "build_native",
 ]

@@ -331,6 +331,23 @@ def retrieve_sharded(targets, local_library, shard_offset, k=10, metric="cd_t", 
     return gather_and_merge(ls, li, k, group=group)
 
 
+class PendingResult:
+    """Result of `RetrievalEngine.submit`: produced on one of the engine's lane streams; `result()` makes the caller's current
+    stream wait for it (no host synchronisation) and hands the tensors over."""
+
+    def __init__(self, tensors, event=None, stream=None):
+        self._tensors, self._event, self._stream = tensors, event, stream
+
+    def result(self):
+        if self._event is not None:
+            cur = torch.cuda.current_stream(self._tensors[0].device)
+            cur.wait_event(self._event)
+            for t in self._tensors:
+                t.record_stream(cur)          # allocated on the lane stream, consumed on the caller's
+            self._event = None
+        return self._tensors
+
+
 class RetrievalEngine:
     """Resident library shard + a CUDA graph of the whole per-query-batch pipeline.
 
@@ -345,10 +362,16 @@ class RetrievalEngine:
       "nccl"  top-k kernel, `all_gather_into_tensor`, merge kernel (the plain collective; also captured).
     Every rank ends with the same (scores [Q, k], global shape ids int32 [Q, k]).  Results are fresh tensors (the graph's
     static outputs are cloned), so a caller may hold them across queries.
+
+    pipeline_depth > 1: that many lanes -- each its own stream, static buffers, graph and exchange buffers, all sharing the
+    resident library -- take the submitted query batches in turn, so the next batch's nn_kernel fills the SMs while the previous
+    batch's tail (the last partial wave of CTAs, dcd_fwd, the exchange's wait for its peers, the result copy) drains.  Use
+    ``submit(targets) -> PendingResult`` to keep batches in flight; ``query()`` is submit + result (one batch at a time).
+    Every rank must submit the same sequence of batches (the lanes exchange with their counterparts on the peers).
     """
 
     def __init__(self, local_library, shard_offset, num_queries, k=10, metric="cd_t", alpha=1000, n_lambda=1,
-                 group=None, use_graph=True, max_pairs=16384, exchange="peer", exact_ranking=False):
+                 group=None, use_graph=True, max_pairs=16384, exchange="peer", exact_ranking=False, pipeline_depth=1):
         if local_library is None:
             self.lib = None
         elif isinstance(local_library, PackedClouds):
@@ -367,6 +390,12 @@ class RetrievalEngine:
         self.static_in = None
         self.kernels_per_replay = 0
         self.use_graph = use_graph
+        self.depth = max(1, int(pipeline_depth))
+        self.lanes, self.lane_streams, self._next = [], [], 0
+        if self.depth > 1:
+            self.lanes = [RetrievalEngine(self.lib, shard_offset, num_queries, k=k, metric=metric, alpha=alpha, n_lambda=n_lambda, group=group,
+                                          use_graph=use_graph, max_pairs=max_pairs, exchange=exchange, exact_ranking=exact_ranking)
+                          for _ in range(self.depth)]
 
     def _peer(self, device):
         if self.xchg is None:
@@ -403,8 +432,42 @@ class RetrievalEngine:
         allmsg = out.view(self.world, Q, k, 2).permute(1, 0, 2, 3).reshape(Q, -1, 2)
         return merge_topk(allmsg[..., 0].contiguous().view(torch.float32), allmsg[..., 1].contiguous(), k)
 
+    def submit(self, targets, host_out=None):
+        """Enqueue one query batch; returns a PendingResult.  With pipeline_depth lanes, consecutive batches overlap on the GPU.
+        host_out: optional (scores, ids) pinned host tensors [Q, k]; the results are also copied there on the lane's stream."""
+        if self.depth == 1:
+            out = self._run(targets)
+            if host_out is not None:
+                host_out[0].copy_(out[0], non_blocking=True)
+                host_out[1].copy_(out[1], non_blocking=True)
+            return PendingResult(out)
+        dev = targets.device
+        if not self.lane_streams:
+            self.lane_streams = [torch.cuda.Stream(device=dev) for _ in range(self.depth)]
+        lane, stream = self.lanes[self._next], self.lane_streams[self._next]
+        self._next = (self._next + 1) % self.depth
+        stream.wait_stream(torch.cuda.current_stream(dev))      # the targets are ready on the caller's stream
+        with torch.cuda.stream(stream):
+            out = lane._run(targets)
+            if host_out is not None:
+                host_out[0].copy_(out[0], non_blocking=True)
+                host_out[1].copy_(out[1], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(stream)
+        targets.record_stream(stream)
+        self.kernels_per_replay = lane.kernels_per_replay
+        return PendingResult(out, done, stream)
+
+    def drain(self):
+        """Make the caller's current stream wait for everything submitted so far (no host synchronisation)."""
+        for st in self.lane_streams:
+            torch.cuda.current_stream(st.device).wait_stream(st)
+
     def query(self, targets):
         """targets [Q, N, 3] float32 CUDA -> (scores [Q, k], global shape ids int32 [Q, k]), identical on all ranks."""
+        return self.submit(targets).result()
+
+    def _run(self, targets):
         if targets.shape[0] != self.Q:
             raise ValueError(f"engine was built for {self.Q} queries per call")
         if not self.use_graph:
@@ -437,12 +500,21 @@ class RetrievalEngine:
             return both[0].view(torch.float32), both[1]
         return tuple(t.clone() for t in self.static_out)
 
+    @property
+    def exchange_mapping(self):
+        x = self.lanes[0].xchg if self.lanes else self.xchg
+        return x.mapping if x is not None else None
+
     def check(self):
         """Synchronise; raise if a peer exchange timed out (ids would be -2)."""
+        for lane in self.lanes:
+            lane.check()
         if self.xchg is not None:
             self.xchg.check()
 
     def close(self):
+        for lane in self.lanes:
+            lane.close()
         if self.xchg is not None:
             self.xchg.close()
             self.xchg = None

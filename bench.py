@@ -209,14 +209,17 @@ class Ctx:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(self, fn, steps, warmup, sampler=None, whole_loop=False, flush=True, collective=True):
+    def timed(self, fn, steps, warmup, sampler=None, whole_loop=False, flush=True, collective=True, finish=None):
         """W untimed warm-up steps, then EXACTLY `steps` timed ones, bracketed by barrier + synchronize, CUDA events on
         the launching stream, max over ranks.  flush: rewrite a 256 MiB buffer between timed iterations (outside the
         event pairs); whole_loop: one event pair around all steps (pipelined e2e loops).  collective=False: this rank
-        alone is measuring (no barrier, no max)."""
+        alone is measuring (no barrier, no max).  finish: called after the last step, before the end event (whole_loop only) --
+        work submitted to other streams is joined into the timed region there."""
         torch = self.torch
         for _ in range(warmup):
             fn()
+        if finish:
+            finish()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(1 if whole_loop else steps)]
         self.barrier() if collective else torch.cuda.synchronize()
         if sampler:
@@ -226,6 +229,8 @@ class Ctx:
             ev[0][0].record()
             for _ in range(steps):
                 fn()
+            if finish:
+                finish()
             ev[0][1].record()
         else:
             for s in range(steps):
@@ -326,7 +331,7 @@ def library_rows(lo, hi, n, dev):
     return torch.cat(slabs) if slabs else None
 
 
-def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, use_graph=True):
+def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, use_graph=True, pipeline_depth=2):
     """One sharded-retrieval workload: every rank scores its shard of the library, ONE fused kernel exchanges and merges
     the top-k.  Strong scaling.  Rank 0 also holds the whole library and produces, in the same run, the 1-rank time
     and the 1-rank answer; the sharded ids must equal it (asserted) on every rank."""
@@ -342,46 +347,53 @@ def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, 
     _, tg_host = synth(Q, 8, n, seed=99)          # same targets on every rank
     tg_pin = tg_host.pin_memory()
     tg_dev = tg_pin.to(dev)
-    out_s = torch.empty(Q, k).pin_memory()
-    out_i = torch.empty(Q, k, dtype=torch.int32).pin_memory()
     pairs_per_step = 2.0 * Q * S * n * n
     note = None
+    # Query batches stream in: two lanes (streams + graphs + exchange buffers) keep two batches in flight, so the next batch's
+    # nn_kernel fills the SMs while the previous batch's tail, epilogue and exchange drain.  Heavy steps (compute-bound for
+    # tens of milliseconds) gain nothing from that and run on one lane.
+    depth = 1 if (heavy or pipeline_depth < 2) else pipeline_depth
     try:
-        engine = ured.RetrievalEngine(shard, lo, Q, k=k, metric="cd_t", use_graph=use_graph, exchange=exchange)
-        v, i = engine.query(tg_dev)
+        engine = ured.RetrievalEngine(shard, lo, Q, k=k, metric="cd_t", use_graph=use_graph, exchange=exchange, pipeline_depth=depth)
+        for _ in range(depth):
+            v, i = engine.query(tg_dev)
         engine.check()
     except ured.NativeLibraryError as exc:        # peer mapping refused on this box: time the NCCL exchange and say so
         if exchange != "peer" or ctx.world == 1:
             raise
         note = f"peer mapping unavailable ({exc}); NCCL all_gather exchange timed instead"
         exchange = "nccl"
-        engine = ured.RetrievalEngine(shard, lo, Q, k=k, metric="cd_t", use_graph=use_graph, exchange="nccl")
-        v, i = engine.query(tg_dev)
+        engine = ured.RetrievalEngine(shard, lo, Q, k=k, metric="cd_t", use_graph=use_graph, exchange="nccl", pipeline_depth=depth)
+        for _ in range(depth):
+            v, i = engine.query(tg_dev)
+    host = [(torch.empty(Q, k).pin_memory(), torch.empty(Q, k, dtype=torch.int32).pin_memory()) for _ in range(depth)]
+    state = {"i": 0}
 
     def step_device():
-        return engine.query(tg_dev)
+        engine.submit(tg_dev)
 
     def step_e2e():
         t = tg_pin.to(dev, non_blocking=True)
-        vv, ii = engine.query(t)
-        out_s.copy_(vv, non_blocking=True)
-        out_i.copy_(ii, non_blocking=True)
+        engine.submit(t, host_out=host[state["i"] % depth])
+        state["i"] += 1
 
-    ms_step, launches = ctx.timed(step_device, st_n, wu_n, flush=False)
-    ms_e2e, _ = ctx.timed(step_e2e, st_n, wu_n, flush=False)
-    v, i = step_device()
+    ms_step, launches = ctx.timed(step_device, st_n, wu_n, flush=False, whole_loop=True, finish=engine.drain)
+    ms_e2e, _ = ctx.timed(step_e2e, st_n, wu_n, flush=False, whole_loop=True, finish=engine.drain)
+    ms_query, _ = ctx.timed(lambda: engine.query(tg_dev), st_n, wu_n, flush=False)      # one batch at a time: the latency of a query
+    v, i = engine.query(tg_dev)
     engine.check()
     torch.cuda.synchronize()
     ids = i.cpu().contiguous()
     sha = hashlib.sha1(ids.numpy().tobytes()).hexdigest()
     rec = {"workload": f"{name}: {desc}", "library_shapes": S, "queries": Q, "points": n, "top_k": k, "n_gpus": ctx.world,
-           "scaling": "strong", "steps": st_n, "warmup": wu_n, "ms_per_step": ms_step,
+           "scaling": "strong", "steps": st_n, "warmup": wu_n, "ms_per_step": ms_step, "pipeline_depth": depth,
+           "ms_per_query_one_at_a_time": ms_query,
            "value": pairs_per_step / (ms_step * 1e-3) / 1e9, "unit": UNIT,
            "e2e": {"ms_per_step": ms_e2e, "value": pairs_per_step / (ms_e2e * 1e-3) / 1e9, "h2d_bytes_per_step": int(tg_pin.numel() * 4),
                    "d2h_bytes_per_step": int(Q * k * 8)},
            "engine": "cuda-graph" if use_graph else "eager",
            "exchange": ("none (1 rank)" if ctx.world == 1 else
-                        (f"fused top-k + peer stores + merge in one kernel ({engine.xchg.mapping})" if exchange == "peer"
+                        (f"fused top-k + peer stores + merge in one kernel ({engine.exchange_mapping})" if exchange == "peer"
                          else "top-k kernel + NCCL all_gather + merge kernel")),
            "kernels_per_step": engine.kernels_per_replay if use_graph else launches // max(st_n, 1),
            "ids_sha1": sha, "top1": {"score": float(v[0, 0]), "id": int(i[0, 0])},
@@ -394,13 +406,15 @@ def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, 
         one = {}
         if ctx.rank == 0:
             full = ured.PackedClouds(library_rows(0, S, n, dev))
-            e1 = ured.RetrievalEngine(full, 0, Q, k=k, metric="cd_t", use_graph=use_graph, exchange="peer")
-            e1.world, e1.exchange = 1, "none"          # a single-rank engine inside a multi-rank job
+            e1 = ured.RetrievalEngine(full, 0, Q, k=k, metric="cd_t", use_graph=use_graph, exchange="peer", pipeline_depth=depth)
+            for e in [e1] + e1.lanes:
+                e.world, e.exchange = 1, "none"        # a single-rank engine inside a multi-rank job
             st_1, wu_1 = (2, 1) if heavy else (st_n, wu_n)
-            ms_1, _ = ctx.timed(lambda: e1.query(tg_dev), st_1, wu_1, flush=False, collective=False)
+            ms_1, _ = ctx.timed(lambda: e1.submit(tg_dev), st_1, max(wu_1, depth), flush=False, collective=False, whole_loop=True, finish=e1.drain)
+            ms_1q, _ = ctx.timed(lambda: e1.query(tg_dev), st_1, wu_1, flush=False, collective=False)
             v1, i1 = e1.query(tg_dev)
             torch.cuda.synchronize()
-            one = {"ms": ms_1, "sha": hashlib.sha1(i1.cpu().contiguous().numpy().tobytes()).hexdigest(), "steps": st_1,
+            one = {"ms": ms_1, "ms_query": ms_1q, "sha": hashlib.sha1(i1.cpu().contiguous().numpy().tobytes()).hexdigest(), "steps": st_1,
                    "scores_equal": bool(torch.equal(v1.cpu(), v.cpu()))}
             del e1, full
         box = [one]
@@ -409,6 +423,7 @@ def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, 
         shas = [None] * ctx.world
         dist.all_gather_object(shas, sha)
         rec["ms_per_step_1rank"] = one["ms"]
+        rec["ms_per_query_one_at_a_time_1rank"] = one["ms_query"]
         rec["steps_1rank"] = one["steps"]
         rec["ids_sha1_1rank"] = one["sha"]
         rec["ids_identical_on_all_ranks"] = all(s_ == sha for s_ in shas)
@@ -418,6 +433,7 @@ def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, 
             raise SystemExit(f"bench.py: sharded retrieval {name} at {ctx.world} ranks does not reproduce the 1-rank ranking: {rec}")
     else:
         rec["ms_per_step_1rank"] = ms_step
+        rec["ms_per_query_one_at_a_time_1rank"] = ms_query
         rec["ids_sha1_1rank"] = sha
         rec["ids_match_1rank"] = True
     engine.close()
@@ -584,6 +600,7 @@ def main():
     ap.add_argument("--queries", type=int, default=0, help="override Q for a stand-alone retrieval workload")
     ap.add_argument("--eager", action="store_true", help="retrieval: eager calls instead of the CUDA-graph engine")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="retrieval on >1 rank: fused peer-memory exchange or NCCL all_gather")
+    ap.add_argument("--pipeline-depth", type=int, default=2, help="retrieval: query batches kept in flight (lanes of the engine); 1 = one at a time")
     ap.add_argument("--exact-only", action="store_true", help="disable the screening pass (difference form on every pair)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload: no cfg1/cfg4 sub-records, reference-op leg or retrieval record")
@@ -606,7 +623,7 @@ def main():
 
     if args.workload in RETRIEVAL:   # stand-alone retrieval run (development): its record is the line
         rec = retrieval_record(ctx, args.workload, args.steps, args.warmup, exchange=args.exchange, S=args.library_size or None,
-                               Q=args.queries or None, use_graph=not args.eager)
+                               Q=args.queries or None, use_graph=not args.eager, pipeline_depth=args.pipeline_depth)
         if ctx.rank == 0:
             print(json.dumps(rec), flush=True)
         if ctx.world > 1:
@@ -649,7 +666,7 @@ def main():
         torch.cuda.empty_cache()
         retr = {}
         for name in ("cfg3", "cfg5"):
-            retr[name] = retrieval_record(ctx, name, args.steps, args.warmup, exchange=args.exchange)
+            retr[name] = retrieval_record(ctx, name, args.steps, args.warmup, exchange=args.exchange, pipeline_depth=args.pipeline_depth)
         line["retrieval"] = retr
     if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
         sample_pairs = 32 if n_x * n_gt <= 2048 * 2048 else 1

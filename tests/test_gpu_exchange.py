@@ -152,8 +152,18 @@ def _rank_main(rank, world, port, out_dir):
             eng.check()
             res[mode] = torch.stack(ids)
             if exchange == "peer":
-                res["mapping"] = eng.xchg.mapping
+                res["mapping"] = eng.exchange_mapping
             eng.close()
+        # two batches in flight: each lane exchanges through its own buffers with its counterpart on the peer
+        eng = ured.RetrievalEngine(shard, lo, Q, k=k, metric="cd_t", exchange="peer", pipeline_depth=2)
+        pend = []
+        for rep in range(4):
+            _, tg = synth(Q, 8, n, seed=40 + rep)
+            pend.append(eng.submit(tg.to(dev)))
+        eng.drain()
+        res["peer-pipelined"] = torch.stack([p.result()[1].cpu() for p in pend])
+        eng.check()
+        eng.close()
         if rank == 0:
             full = library_rows(0, S, n, dev)
             want = []
@@ -174,7 +184,7 @@ def test_sharded_engine_two_real_ranks(ured, tmp_path):
     res = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
     want = res[0]["want"]
     for r in res:
-        for mode in ("peer-eager", "peer-graph", "nccl-eager"):
+        for mode in ("peer-eager", "peer-graph", "nccl-eager", "peer-pipelined"):
             assert torch.equal(r[mode], want), f"{mode}: sharded ids differ from the one-rank ranking"
 
 

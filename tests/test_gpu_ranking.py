@@ -155,3 +155,28 @@ def test_engine_metric_selection_and_exact_ranking(ured, oracle, ref_op):
     keep = (first[0].clone(), first[1].clone())
     again.query(make_clouds(402, 2, n, "S").cuda())
     assert torch.equal(first[0], keep[0]) and torch.equal(first[1], keep[1])
+
+
+def test_pipelined_engine_equals_one_at_a_time(ured):
+    """pipeline_depth=2: batches submitted back to back on alternating lanes return exactly what query() returns for each batch,
+    in submission order, also when the results are picked up late and when they are copied to pinned host memory by the lane."""
+    S, n, k, Q = 400, 2048, 10, 2
+    lib_x = make_clouds(410, S, n, "S").cuda()
+    batches = [make_clouds(420 + j, Q, n, "S").cuda() for j in range(7)]
+    plain = ured.RetrievalEngine(lib_x, 0, Q, k=k)
+    want = [tuple(t.clone() for t in plain.query(b)) for b in batches]
+    piped = ured.RetrievalEngine(lib_x, 0, Q, k=k, pipeline_depth=2)
+    assert len(piped.lanes) == 2 and piped.lanes[0].lib is piped.lib       # the library is shared, not copied
+    host = [(torch.empty(Q, k).pin_memory(), torch.empty(Q, k, dtype=torch.int32).pin_memory()) for _ in batches]
+    pend = [piped.submit(b, host_out=h) for b, h in zip(batches, host)]
+    piped.drain()
+    torch.cuda.synchronize()
+    for j, (p, w) in enumerate(zip(pend, want)):
+        got = p.result()
+        assert torch.equal(got[0], w[0]) and torch.equal(got[1], w[1]), f"batch {j}"
+        assert torch.equal(host[j][0], w[0].cpu()) and torch.equal(host[j][1], w[1].cpu()), f"batch {j} (host copy)"
+    for b, w in zip(batches[:3], want):                                   # query() on a pipelined engine: one at a time
+        got = piped.query(b)
+        assert torch.equal(got[1], w[1])
+    piped.check()
+    piped.close()
