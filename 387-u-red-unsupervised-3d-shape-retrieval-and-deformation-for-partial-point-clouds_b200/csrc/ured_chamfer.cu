@@ -990,10 +990,11 @@ __device__ __forceinline__ float point_grad_coeff(const GradParams &p, int side,
     return gd;
 }
 
-// in-place exclusive prefix sum of a[0..n) by the whole CTA (kGradSmemThreads threads); scratch: 33 ints
+// in-place exclusive prefix sum of a[0..n) by the whole CTA (THREADS threads); scratch: 33 ints
+template <int THREADS>
 __device__ __forceinline__ void block_exclusive_scan(int *a, int n, int *scratch) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + kGradSmemThreads - 1) / kGradSmemThreads;
+    const int per = (n + THREADS - 1) / THREADS;
     const int lo = min(n, tid * per), hi = min(n, lo + per);
     int sum = 0;
     for (int k = lo; k < hi; k++) sum += a[k];
@@ -1006,7 +1007,7 @@ __device__ __forceinline__ void block_exclusive_scan(int *a, int n, int *scratch
     if (lane == 31) scratch[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        int w = lane < kGradSmemThreads / 32 ? scratch[lane] : 0;
+        int w = lane < THREADS / 32 ? scratch[lane] : 0;
         int winc = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1136,8 +1137,8 @@ __global__ void __launch_bounds__(kGradSmemThreads, 3) grad_gather_kernel(const 
     for (int i = tid; i < q2; i += kGradSmemThreads) atomicAdd(&seg[n2 + idx2[i]], 1);
     __syncthreads();
     // ---- 2. segment starts ------------------------------------------------------------------------------------------
-    block_exclusive_scan(seg, n2, scan_scratch);
-    block_exclusive_scan(seg + n2, n1, scan_scratch);
+    block_exclusive_scan<kGradSmemThreads>(seg, n2, scan_scratch);
+    block_exclusive_scan<kGradSmemThreads>(seg + n2, n1, scan_scratch);
     // ---- 3. own terms + grouping ------------------------------------------------------------------------------------
     GradSide s1, s2;
     s1.xyz_own = xyz1; s1.xyz_oth = xyz2; s1.idx = idx1; s1.v_own = v1;
@@ -1162,6 +1163,144 @@ __global__ void __launch_bounds__(kGradSmemThreads, 3) grad_gather_kernel(const 
     // cloud-1 point j was chosen by the cloud-2 points filed in bins seg[n2 + j]; cloud-2 point j by the cloud-1 points in seg[j]
     grad_gather_side(vec, vec + n1 * 3, n1, seg + n2, lst + n1, idx2, q2, p.grad[0] + b * n1 * 3);
     grad_gather_side(vec + n1 * 3, vec, n2, seg, lst, idx1, v1, p.grad[1] + b * n2 * 3);
+}
+
+// ---- one CTA per (pair, cloud) --------------------------------------------------------------------------------------
+// The CTA that writes the gradient of cloud `s` needs, in shared memory, only the OTHER cloud's own terms (they are fetched
+// through the lists) plus the bins over its own points; the own term of the point a thread is finishing is evaluated in
+// registers from global memory.  That is 14 bytes per point of the other cloud + 4 per own point -- 36 KB for 2048 + 2048,
+// six CTAs per SM instead of three, and twice as many, half as long CTAs (a 32-pair training batch fills 64 SMs, not 32).
+// Every own term is evaluated twice (once by each CTA of the pair) by the same code, so both see the same bits; the
+// subtraction order (own term, then the choosers in ascending index) is the one of grad_gather_kernel.
+struct OwnTerm { float x, y, z; int j2; };
+template <int U, int THREADS>
+__device__ __forceinline__ void grad_term_batch(const GradSide &sd, int base, OwnTerm (&t)[U]) {
+    int j2[U];
+    float gd[U], ax[U], ay[U], az[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int j = base + u * THREADS;
+        const bool ok = j < sd.v_own;
+        j2[u] = ok ? sd.idx[j] : -1;
+        ax[u] = ok ? sd.xyz_own[j * 3 + 0] : 0.0f; ay[u] = ok ? sd.xyz_own[j * 3 + 1] : 0.0f; az[u] = ok ? sd.xyz_own[j * 3 + 2] : 0.0f;
+        float g = (ok && sd.g_dist) ? sd.g_dist[j] : 0.0f;
+        if (sd.k_t != 0.0f) g += sd.k_t;
+        if (sd.dist) g += sd.k_p * (0.5f / sqrtf(ok ? sd.dist[j] : 1.0f));
+        if (sd.ew) g += sd.k_l * (sd.alpha * (ok ? sd.ew[j] : 0.0f));
+        gd[u] = g;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int k = max(j2[u], 0);
+        const float ox = sd.xyz_oth[k * 3 + 0], oy = sd.xyz_oth[k * 3 + 1], oz = sd.xyz_oth[k * 3 + 2];
+        const float g = j2[u] >= 0 ? __fmul_rn(gd[u], 2.0f) : 0.0f;  // chamfer3D.cu:166
+        t[u].x = __fmul_rn(g, __fsub_rn(ax[u], ox));
+        t[u].y = __fmul_rn(g, __fsub_rn(ay[u], oy));
+        t[u].z = __fmul_rn(g, __fsub_rn(az[u], oz));
+        t[u].j2 = j2[u];
+    }
+}
+
+__device__ __forceinline__ void grad_side_setup(const GradParams &p, size_t b, int s, int v_search, int v_norm, GradSide &sd) {
+    const int n_own = p.n[s], n_oth = p.n[1 - s];
+    sd.xyz_own = p.xyz[s] + b * n_own * 3; sd.xyz_oth = p.xyz[1 - s] + b * n_oth * 3;
+    sd.idx = p.idx[s] ? p.idx[s] + b * n_own : nullptr;
+    sd.v_own = v_search;
+    sd.g_dist = p.g_dist[s] ? p.g_dist[s] + b * n_own : nullptr;
+    sd.dist = p.g_cd_p ? p.dist[s] + b * n_own : nullptr;
+    sd.ew = p.g_loss ? p.ew[s] + b * n_own : nullptr;
+    sd.k_t = p.g_cd_t ? p.g_cd_t[b] / (float)max(v_norm, 1) : 0.0f;
+    sd.k_p = p.g_cd_p ? p.g_cd_p[b] * 0.5f / (float)max(v_norm, 1) : 0.0f;
+    sd.k_l = p.g_loss ? p.g_loss[b] * 0.5f / (float)max(v_norm, 1) : 0.0f;
+    sd.alpha = p.alpha;
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) grad_side_kernel(const GradParams p) {
+    extern __shared__ float gsm[];
+    __shared__ int scan_scratch[33];
+    const size_t b = blockIdx.x >> 1;
+    const int s = blockIdx.x & 1;                        // the cloud whose gradient this CTA writes
+    const int tid = threadIdx.x;
+    const int n_own = p.n[s], n_oth = p.n[1 - s];
+    float *vec = gsm;                                            // [n_oth * 3] own terms of the other cloud's points
+    int *seg = reinterpret_cast<int *>(gsm + (size_t)n_oth * 3);  // [n_own]     bins over this cloud's points
+    grad_idx_t *lst = reinterpret_cast<grad_idx_t *>(seg + n_own);   // [n_oth] the other cloud's points grouped by their choice
+    int v1 = valid_len(p.len[0], b, p.n[0]), v2 = valid_len(p.len[1], b, p.n[1]);
+    if (v1 == 0 || v2 == 0) { v1 = 0; v2 = 0; }          // an empty side: no matches, zero gradients
+    const int q2 = p.one_dir ? 0 : v2;                   // cloud-2 points that searched cloud 1
+    const int s_own = s ? q2 : v1, s_oth = s ? v1 : q2;  // searching points of this cloud / of the other one
+    GradSide own, oth;
+    grad_side_setup(p, b, s, s_own, s ? v2 : v1, own);
+    grad_side_setup(p, b, 1 - s, s_oth, s ? v1 : v2, oth);
+
+    // ---- 1. histogram of the other cloud's argmins (bins = this cloud's points) -----------------------------------------
+    for (int k = tid; k < n_own; k += THREADS) seg[k] = 0;
+    __syncthreads();
+#pragma unroll 4
+    for (int i = tid; i < s_oth; i += THREADS) atomicAdd(&seg[oth.idx[i]], 1);
+    __syncthreads();
+    // ---- 2. segment starts ------------------------------------------------------------------------------------------------
+    block_exclusive_scan<THREADS>(seg, n_own, scan_scratch);
+    // ---- 3. the other cloud's own terms, filed under the point each one chose (seg[bin] ends as the END of the bin) -------
+    {
+        constexpr int U = 4;
+        for (int base = tid; base < s_oth; base += THREADS * U) {
+            OwnTerm t[U];
+            grad_term_batch<U, THREADS>(oth, base, t);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = base + u * THREADS;
+                if (t[u].j2 >= 0) {
+                    vec[i * 3 + 0] = t[u].x; vec[i * 3 + 1] = t[u].y; vec[i * 3 + 2] = t[u].z;
+                    lst[atomicAdd(&seg[t[u].j2], 1)] = (grad_idx_t)i;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 4. this cloud's points: own term minus, in ascending index order, the terms of the points that chose it ---------
+    constexpr int kNone = 0x7fffffff;
+    constexpr int UG = 2;
+    float *grad_out = p.grad[s] + b * n_own * 3;
+    for (int base = tid; base < n_own; base += THREADS * UG) {
+        OwnTerm t[UG];
+        grad_term_batch<UG, THREADS>(own, base, t);
+#pragma unroll
+        for (int u = 0; u < UG; u++) {
+            const int j = base + u * THREADS;
+            if (j >= n_own) continue;
+            const int start = j == 0 ? 0 : seg[j - 1], end = seg[j];
+            const int len = end - start;
+            float ax = t[u].x, ay = t[u].y, az = t[u].z;
+            if (len <= 4) {
+                int a0 = len > 0 ? (int)lst[start] : kNone, a1 = len > 1 ? (int)lst[start + 1] : kNone;
+                int a2 = len > 2 ? (int)lst[start + 2] : kNone, a3 = len > 3 ? (int)lst[start + 3] : kNone;
+#define URED_CSWAP(x, y) { const int lo_ = min(x, y), hi_ = max(x, y); x = lo_; y = hi_; }
+                URED_CSWAP(a0, a1) URED_CSWAP(a2, a3) URED_CSWAP(a0, a2) URED_CSWAP(a1, a3) URED_CSWAP(a1, a2)
+#undef URED_CSWAP
+                if (a0 != kNone) { ax = __fsub_rn(ax, vec[a0 * 3 + 0]); ay = __fsub_rn(ay, vec[a0 * 3 + 1]); az = __fsub_rn(az, vec[a0 * 3 + 2]); }
+                if (a1 != kNone) { ax = __fsub_rn(ax, vec[a1 * 3 + 0]); ay = __fsub_rn(ay, vec[a1 * 3 + 1]); az = __fsub_rn(az, vec[a1 * 3 + 2]); }
+                if (a2 != kNone) { ax = __fsub_rn(ax, vec[a2 * 3 + 0]); ay = __fsub_rn(ay, vec[a2 * 3 + 1]); az = __fsub_rn(az, vec[a2 * 3 + 2]); }
+                if (a3 != kNone) { ax = __fsub_rn(ax, vec[a3 * 3 + 0]); ay = __fsub_rn(ay, vec[a3 * 3 + 1]); az = __fsub_rn(az, vec[a3 * 3 + 2]); }
+            } else if (len <= kGradSortMax) {
+                for (int w0 = start + 1; w0 < end; w0++) {          // insertion sort of a short, thread-private segment
+                    const grad_idx_t key = lst[w0];
+                    int w = w0 - 1;
+                    while (w >= start && lst[w] > key) { lst[w + 1] = lst[w]; w--; }
+                    lst[w + 1] = key;
+                }
+                for (int w0 = start; w0 < end; w0++) {
+                    const int i = lst[w0];
+                    ax = __fsub_rn(ax, vec[i * 3 + 0]); ay = __fsub_rn(ay, vec[i * 3 + 1]); az = __fsub_rn(az, vec[i * 3 + 2]);
+                }
+            } else {
+                for (int i = 0; i < s_oth; i++)                  // ascending scan of the other cloud's argmins
+                    if (oth.idx[i] == j) { ax = __fsub_rn(ax, vec[i * 3 + 0]); ay = __fsub_rn(ay, vec[i * 3 + 1]); az = __fsub_rn(az, vec[i * 3 + 2]); }
+            }
+            grad_out[j * 3 + 0] = ax; grad_out[j * 3 + 1] = ay; grad_out[j * 3 + 2] = az;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1928,6 +2067,28 @@ int ured_dcd_backward(const float *xyz1, const float *xyz2, int B, int n1, int n
     p.alpha = alpha;
     p.len[0] = len1; p.len[1] = len2;
     p.one_dir = idx2 ? 0 : 1;   // (ured_nn_backward_one_direction passes no idx2)
+    // one CTA per (pair, cloud): 14 B per point of the other cloud + 4 B per own point (6 CTAs per SM at 2048 + 2048)
+    const size_t side_need = (size_t)max(n1, n2) * 14 + (size_t)min(n1, n2) * 4;
+    // Measured (profiles/README.md, round 2).  640 pairs: the pair kernel is faster (62 us against 91 us -- every own term is
+    // evaluated twice here).  32 pairs: a lone CTA's time is its threads' serial work, so 64 CTAs of 1024 threads finish in
+    // 15 us where 32 CTAs of 512 threads take 24 us (and 64 CTAs of 256 threads 26 us).  So: this kernel, wide, while its
+    // 2 B CTAs get an SM each; also when a pair does not fit one CTA's shared memory but each side does.
+    const int pair_cta = env_int("URED_GRAD_PAIR_CTA", -1);   // tests / A-B runs: 1 forces the per-pair kernel, 0 this one
+    const size_t pair_need = (size_t)(n1 + n2) * 18;
+    const bool few = 2ll * B <= 148;                          // 148 SMs (B200)
+    const bool prefer_side = pair_cta >= 0 ? pair_cta == 0 : (few || pair_need > 200 * 1024);
+    if (prefer_side && !shared1 && !shared2 && side_need <= 200 * 1024 && max(n1, n2) < 65536 && !(flags_env_general())) {
+        const int wide_env = env_int("URED_GRAD_SIDE_WIDE", -1);
+        const bool big = wide_env >= 0 ? wide_env != 0 : (few || side_need > 72 * 1024);   // (fewer than 3 narrow CTAs per SM would fit)
+        if (side_need > kSmemOptIn) {
+            if (big) URED_CUDA(cudaFuncSetAttribute(grad_side_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "grad smem attribute");
+            else URED_CUDA(cudaFuncSetAttribute(grad_side_kernel<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "grad smem attribute");
+        }
+        if (big) grad_side_kernel<1024, 1><<<2 * (unsigned)B, 1024, side_need, st>>>(p);
+        else grad_side_kernel<256, 6><<<2 * (unsigned)B, 256, side_need, st>>>(p);
+        URED_COUNT_LAUNCH();
+        return check_cuda(cudaGetLastError(), "grad_side_kernel launch");
+    }
     const size_t smem_need = (size_t)(n1 + n2) * 18;  // own terms (12 B) + segment ends (4 B) + lists (2 B) per point: 3 CTAs per SM at 2048 + 2048
     if (!shared1 && !shared2 && smem_need <= 200 * 1024 && !(flags_env_general())) {
         if (smem_need > kSmemOptIn)

@@ -331,7 +331,7 @@ def library_rows(lo, hi, n, dev):
     return torch.cat(slabs) if slabs else None
 
 
-def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, use_graph=True, pipeline_depth=2):
+def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, use_graph=True, pipeline_depth=3):
     """One sharded-retrieval workload: every rank scores its shard of the library, ONE fused kernel exchanges and merges
     the top-k.  Strong scaling.  Rank 0 also holds the whole library and produces, in the same run, the 1-rank time
     and the 1-rank answer; the sharded ids must equal it (asserted) on every rank."""
@@ -600,7 +600,7 @@ def main():
     ap.add_argument("--queries", type=int, default=0, help="override Q for a stand-alone retrieval workload")
     ap.add_argument("--eager", action="store_true", help="retrieval: eager calls instead of the CUDA-graph engine")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="retrieval on >1 rank: fused peer-memory exchange or NCCL all_gather")
-    ap.add_argument("--pipeline-depth", type=int, default=2, help="retrieval: query batches kept in flight (lanes of the engine); 1 = one at a time")
+    ap.add_argument("--pipeline-depth", type=int, default=3, help="retrieval: query batches kept in flight (lanes of the engine); 1 = one at a time")
     ap.add_argument("--exact-only", action="store_true", help="disable the screening pass (difference form on every pair)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload: no cfg1/cfg4 sub-records, reference-op leg or retrieval record")

@@ -404,6 +404,50 @@ def test_backward_is_bit_reproducible_and_handles_crowded_points(ured, oracle):
     assert rel_err(k1.cpu().numpy(), r1) < RTOL and rel_err(k2.cpu().numpy(), r2) < RTOL
 
 
+@pytest.mark.parametrize("B,N,M,ragged", [(3, 2048, 2048, False), (5, 1500, 700, True), (2, 6000, 8000, False), (80, 512, 512, False)])
+def test_gather_backward_kernels_agree_bit_for_bit(ured, B, N, M, ragged):
+    """The three atomic-free backward kernels -- one CTA per pair (grad_gather_kernel), one CTA per (pair, cloud) narrow and
+    wide (grad_side_kernel<256/1024>) -- subtract in the same order (own term, then the choosers by ascending index), so they
+    must return the same bits; the library picks between them by batch size and cloud size (ured_dcd_backward)."""
+    import os
+    a, b = make_clouds(190, B, N, "S"), make_clouds(191, B, M, "S") * 0.9
+    g = torch.Generator().manual_seed(8)
+    w1, w2 = torch.randn(B, N, generator=g), torch.randn(B, M, generator=g)
+    lens = {}
+    if ragged:
+        lens = dict(len_x=torch.randint(1, N + 1, (B,), generator=g).int().cuda(), len_gt=torch.randint(1, M + 1, (B,), generator=g).int().cuda())
+        lens["len_x"][0] = 0
+
+    def grads(env):
+        for k in ("URED_GRAD_PAIR_CTA", "URED_GRAD_SIDE_WIDE"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        try:
+            xa, xb = dev(a).requires_grad_(), dev(b).requires_grad_()
+            if ragged:
+                loss, cd_p, cd_t = ured.chamfer_ragged(xa, xb, alpha=200, n_lambda=0.5, **lens)[:3]
+                (loss.sum() + 0.3 * cd_t.sum() + 0.1 * cd_p.sum()).backward()
+            else:
+                d1, d2, _, _ = ured.chamfer_3DDist()(xa, xb)
+                ((d1 * dev(w1)).sum() + (d2 * dev(w2)).sum()).backward()
+            return xa.grad.clone(), xb.grad.clone()
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+
+    default = grads({})
+    fits_pair = (N + M) * 18 <= 200 * 1024
+    variants = [{"URED_GRAD_PAIR_CTA": "0", "URED_GRAD_SIDE_WIDE": "0"}, {"URED_GRAD_PAIR_CTA": "0", "URED_GRAD_SIDE_WIDE": "1"}]
+    if fits_pair:
+        variants.append({"URED_GRAD_PAIR_CTA": "1"})
+    for env in variants:
+        got = grads(env)
+        assert torch.equal(got[0], default[0]) and torch.equal(got[1], default[1]), f"{env} differs from the default kernel"
+    general = grads({"URED_GRAD_GENERAL": "1"})                 # the global-atomic kernels: same values up to summation order
+    assert rel_err(general[0].cpu().numpy(), default[0].cpu().numpy()) < RTOL
+    assert rel_err(general[1].cpu().numpy(), default[1].cpu().numpy()) < RTOL
+
+
 def test_knn1_and_residual_retrieval_loss(ured, oracle):
     """K=1 kNN (loss/basic_loss.py:249-265's knn_points call) on the one-direction NN kernel, ragged source lengths."""
     B, N, P = 3, 700, 3
