@@ -718,8 +718,8 @@ struct DcdOut {
 // STAGED: the per-point terms are computed by ALL threads (independent, unrolled loads: memory-level parallelism), staged
 // in shared memory next to the histograms, and the six ordered row sums then run over shared memory.  Needs 8 bytes per
 // point; pairs too large for that (more than 25 600 points) compute the terms inside the ordered sums instead.
-template <bool STAGED>
-__global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__restrict__ dist1, const float *__restrict__ dist2,
+template <bool STAGED, int THREADS>
+__global__ void __launch_bounds__(THREADS) dcd_fwd_kernel(const float *__restrict__ dist1, const float *__restrict__ dist2,
                                                               const int *__restrict__ idx1, const int *__restrict__ idx2,
                                                               int n1_max, int n2_max, float alpha, float n_lambda, float frac_12,
                                                               float frac_21, const DcdOut out, const DcdLens lens) {
@@ -741,8 +741,8 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
         if (lens.non_reg) { frac_12 = fmaxf(frac_12, 1.0f); frac_21 = fmaxf(frac_21, 1.0f); }
     }
     if (n1 == 0 || n2 == 0) {  // an empty side: nothing to average (callers mask such pairs out)
-        for (int k = tid; k < n1_max; k += kDcdThreads) if (out.ew1) out.ew1[b * n1_max + k] = 0.0f;
-        for (int k = tid; k < n2_max; k += kDcdThreads) if (out.ew2) out.ew2[b * n2_max + k] = 0.0f;
+        for (int k = tid; k < n1_max; k += THREADS) if (out.ew1) out.ew1[b * n1_max + k] = 0.0f;
+        for (int k = tid; k < n2_max; k += THREADS) if (out.ew2) out.ew2[b * n2_max + k] = 0.0f;
         if (tid == 0) {
             if (out.loss) out.loss[b] = 0.0f;
             if (out.cd_p) out.cd_p[b] = 0.0f;
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
     }
     const bool want_loss = out.loss || out.ew1 || out.ew2;
     if (want_loss) {
-        for (int k = tid; k < nt_max; k += kDcdThreads) hist[k] = 0;
+        for (int k = tid; k < nt_max; k += THREADS) hist[k] = 0;
         __syncthreads();
         // (rows are 16-byte aligned whenever the row stride is a multiple of four points: 128-bit loads, four points per thread and step)
         const bool vec1 = (n1_max & 3) == 0 && (reinterpret_cast<uintptr_t>(i1) & 15u) == 0;
@@ -763,13 +763,13 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
             if (vec) {
                 const int4 *ix4 = reinterpret_cast<const int4 *>(ix);
 #pragma unroll 4
-                for (int q = tid; q < (n >> 2); q += kDcdThreads) {
+                for (int q = tid; q < (n >> 2); q += THREADS) {
                     const int4 v = ix4[q];
                     atomicAdd(&cnt[v.x], 1); atomicAdd(&cnt[v.y], 1); atomicAdd(&cnt[v.z], 1); atomicAdd(&cnt[v.w], 1);
                 }
                 k0 = n & ~3;
             }
-            for (int k = k0 + tid; k < n; k += kDcdThreads) atomicAdd(&cnt[ix[k]], 1);
+            for (int k = k0 + tid; k < n; k += THREADS) atomicAdd(&cnt[ix[k]], 1);
         };
         hist_side(i1, n1, vec1, count1);
         hist_side(i2, n2, vec2, count2);
@@ -786,8 +786,8 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
             // the weight depends on the BIN only: turn the counts into weights in place (one division per bin instead of one
             // per point, no data-dependent work left in the per-point loop), then stream the points of each side
             float *w1 = reinterpret_cast<float *>(count1), *w2 = reinterpret_cast<float *>(count2);
-            for (int j = tid; j < n2_max; j += kDcdThreads) w1[j] = weight_of(count1[j], frac_21);
-            for (int j = tid; j < n1_max; j += kDcdThreads) w2[j] = weight_of(count2[j], frac_12);
+            for (int j = tid; j < n2_max; j += THREADS) w1[j] = weight_of(count1[j], frac_21);
+            for (int j = tid; j < n1_max; j += THREADS) w2[j] = weight_of(count2[j], frac_12);
             __syncthreads();
             const float neg_alpha = -alpha;   // (-d)*alpha == d*(-alpha) bit for bit
             auto terms_side = [&](const float *__restrict__ d, const int *__restrict__ ix, const float *w, float *__restrict__ e, float *t_out,
@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
                     const float4 *d4 = reinterpret_cast<const float4 *>(d);
                     const int4 *ix4 = reinterpret_cast<const int4 *>(ix);
 #pragma unroll 2
-                    for (int q = tid; q < (n >> 2); q += kDcdThreads) {
+                    for (int q = tid; q < (n >> 2); q += THREADS) {
                         const float4 dv = d4[q];
                         const int4 iv = ix4[q];
                         float4 ev;
@@ -811,12 +811,12 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
                     }
                     k0 = n & ~3;
                 }
-                for (int k = k0 + tid; k < n; k += kDcdThreads) {
+                for (int k = k0 + tid; k < n; k += THREADS) {
                     const float ewk = __fmul_rn(expf(__fmul_rn(d[k], neg_alpha)), w[ix[k]]);
                     if (e) e[k] = ewk;
                     t_out[k] = __fsub_rn(1.0f, ewk);
                 }
-                if (e) for (int k = n + tid; k < n_max; k += kDcdThreads) e[k] = 0.0f;   // past the valid length of a ragged cloud
+                if (e) for (int k = n + tid; k < n_max; k += THREADS) e[k] = 0.0f;   // past the valid length of a ragged cloud
             };
             terms_side(d1, i1, w1, out.ew1 ? out.ew1 + b * n1_max : nullptr, term, n1, n1_max, vd1);
             terms_side(d2, i2, w2, out.ew2 ? out.ew2 + b * n2_max : nullptr, term + n1_max, n2, n2_max, vd2);
@@ -827,10 +827,10 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
             int k0 = 0;
             if (vec && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
 #pragma unroll 2
-                for (int q = tid; q < (n_max >> 2); q += kDcdThreads) reinterpret_cast<float4 *>(dst)[q] = reinterpret_cast<const float4 *>(d)[q];
+                for (int q = tid; q < (n_max >> 2); q += THREADS) reinterpret_cast<float4 *>(dst)[q] = reinterpret_cast<const float4 *>(d)[q];
                 k0 = n_max & ~3;
             }
-            for (int k = k0 + tid; k < n_max; k += kDcdThreads) dst[k] = d[k];
+            for (int k = k0 + tid; k < n_max; k += THREADS) dst[k] = d[k];
         };
         copy_side(d1, sd, n1_max, vd1);
         copy_side(d2, sd + n1_max, n2_max, vd2);
@@ -839,8 +839,8 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
     auto ew_of = [&](float dk, int c, float frac) { return __fmul_rn(expf(__fmul_rn(-dk, alpha)), weight_of(c, frac)); };
 
     // warps 0-2: side 1 (term, d, sqrt d); warps 3-5: side 2; warps 6, 7: F-score counts of side 1 / 2
-    const int side = warp < 6 ? warp / 3 : warp - 6;
-    const int what = warp < 6 ? warp % 3 : 3;
+    const int side = warp < 6 ? warp / 3 : (warp - 6) & 1;
+    const int what = warp < 6 ? warp % 3 : (warp < 8 ? 3 : 4);   // (warps past the eighth of a wide CTA have nothing to sum)
     const int n = side ? n2 : n1;
     const int n_stride = side ? n2_max : n1_max;
     const float *d = side ? d2 : d1;
@@ -871,13 +871,13 @@ __global__ void __launch_bounds__(kDcdThreads) dcd_fwd_kernel(const float *__res
         r = STAGED ? torch_row_sum_staged<false>(sdist, n, mis, lane) : torch_row_sum([&](int k) { return d[k]; }, n, mis, lane);
     } else if (what == 2) {
         r = STAGED ? torch_row_sum_staged<true>(sdist, n, mis, lane) : torch_row_sum([&](int k) { return sqrtf(d[k]); }, n, mis, lane);
-    } else if (out.fscore) {
+    } else if (what == 3 && out.fscore) {
         int c = 0;
         for (int k = lane; k < n; k += 32) c += (STAGED ? sdist[k] : d[k]) < out.f_threshold ? 1 : 0;
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         r = (float)c;  // a sum of 0/1 floats is exact in any order
     }
-    if (lane == 0) sums[warp] = r;
+    if (lane == 0 && warp < 8) sums[warp] = r;
     __syncthreads();
     if (tid == 0) {
         // torch's mean: sum * factor with factor = float(outputs) / float(numel) (ReduceMomentKernel.cu mean_kernel_impl);
@@ -2009,20 +2009,24 @@ int ured_dcd_forward_ex(const float *dist1, const float *dist2, const int *idx1,
     const size_t smem = staged ? staged_bytes : (want_loss ? (size_t)(n1 + n2) * sizeof(int) : 0);  // unstaged: cd_p / cd_t / fscore alone need no histogram
     if (smem > 200 * 1024) return fail_arg(URED_E_RANGE, "ured_dcd_forward: n1 + n2 > 51200 points per pair not supported");
     // (per device, not per thread or process: set before every launch that needs it -- the call is cheap and legal during capture)
-    if (smem > kSmemOptIn)
-        URED_CUDA(staged ? cudaFuncSetAttribute(dcd_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
-                         : cudaFuncSetAttribute(dcd_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "dcd smem attribute");
+    const bool wide = B <= 148 && env_int("URED_DCD_WIDE", 1);   // (see the launch below)
+    if (smem > kSmemOptIn) {
+        const void *fn = staged ? (wide ? (const void *)dcd_fwd_kernel<true, 1024> : (const void *)dcd_fwd_kernel<true, kDcdThreads>)
+                                : (wide ? (const void *)dcd_fwd_kernel<false, 1024> : (const void *)dcd_fwd_kernel<false, kDcdThreads>);
+        URED_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "dcd smem attribute");
+    }
     DcdLens lens;
     lens.len1 = len1; lens.len2 = len2; lens.rep1 = rep1; lens.mod2 = mod2; lens.non_reg = (flags & URED_FLAG_NON_REG) ? 1 : 0;
     DcdOut out;
     out.loss = loss; out.cd_p = cd_p; out.cd_t = cd_t; out.ew1 = ew1; out.ew2 = ew2;
     out.fscore = fscore; out.f_threshold = f_threshold; out.B = B;
-    if (staged)
-        dcd_fwd_kernel<true><<<B, kDcdThreads, smem, (cudaStream_t)stream>>>(dist1, dist2, idx1, idx2, n1, n2, alpha, n_lambda, frac_12,
-                                                                             frac_21, out, lens);
-    else
-        dcd_fwd_kernel<false><<<B, kDcdThreads, smem, (cudaStream_t)stream>>>(dist1, dist2, idx1, idx2, n1, n2, alpha, n_lambda, frac_12,
-                                                                              frac_21, out, lens);
+    // A lone CTA's time is its threads' serial work: while every pair gets an SM to itself, 1024 threads per pair finish sooner
+    // (32 pairs: 13 us with 256 threads); with more pairs 256-thread CTAs keep the whole batch in one wave.
+#define URED_DCD_LAUNCH(ST, TH) dcd_fwd_kernel<ST, TH><<<B, TH, smem, (cudaStream_t)stream>>>(dist1, dist2, idx1, idx2, n1, n2, alpha, n_lambda, \
+                                                                                         frac_12, frac_21, out, lens)
+    if (staged) { if (wide) URED_DCD_LAUNCH(true, 1024); else URED_DCD_LAUNCH(true, kDcdThreads); }
+    else { if (wide) URED_DCD_LAUNCH(false, 1024); else URED_DCD_LAUNCH(false, kDcdThreads); }
+#undef URED_DCD_LAUNCH
     URED_COUNT_LAUNCH();
     return check_cuda(cudaGetLastError(), "dcd_fwd_kernel launch");
 }
