@@ -554,6 +554,447 @@ __global__ void __launch_bounds__(256) merge_splits_kernel(const MergeParams m) 
     (dir ? m.idx[1] : m.idx[0])[(size_t)b * nq + j] = i;
 }
 
+// ------------------------------------------------------------------------------------------
+// nearest-neighbour kernel, screening pass on the tensor cores (tcgen05 + TMEM)
+// ------------------------------------------------------------------------------------------
+// The screening scores s = W_c - 2 q.c of nn_kernel<SCREEN> are a [queries x K] . [candidates x K]^T product.  With K = 3 the
+// tensor cores are no use -- unless the operands are made exact in their input type: every fp32 coordinate is split into three
+// bf16 pieces (x = x1 + x2 + x3 exactly: 3 x 8 significant bits), and the product (-2 q_d) c_d is expanded into the eight piece
+// products a_i b_j with i + j <= 5 (the ninth, a_3 b_3, is below 2^-32 of the product); W_c enters as its three pieces times
+// 1.0.  That is 27 exact bf16 x bf16 products per pair, K padded to 32, accumulated in fp32 by tcgen05.mma kind::f16
+// (M = 128 queries, N = 256 candidates, two K = 16 instructions per tile).  Measured on the B200 (tools/microbench/tc_probe.cu,
+// profiles/r02_tc_probe.txt): |s_tc - s_exact| <= 2^-23.2 S^2 on unit-ball clouds and 2^-24.1 S^2 on clouds shifted by +1000,
+// i.e. inside the 6 u S^2 the fp32 FMA chain is allowed (DESIGN.md "screening bound"), so the SAME eps = 32 u S^2 decides
+// ambiguity and everything downstream -- the exact difference-form re-check of the winning 32-candidate chunk, the
+// warp-cooperative exact rescan of ambiguous queries, the lowest-index tie rule -- is nn_kernel's.  Output bits are identical.
+//
+// One persistent CTA per SM.  Work item = (pair, direction, group of query tiles); per item the candidate cloud's operand image
+// (64 B per point, canonical K-major no-swizzle core-matrix layout) is built ONCE in shared memory and stays resident with the
+// fp32 X|Y|Z arrays (TMA bulk copy) for the re-check.  Warps 0-3 own one query each (TMEM lane = query = accumulator row):
+// they write the query tile's operand rows, read the [128 x 256] accumulator 32 columns (= one candidate chunk) at a time with
+// tcgen05.ld, keep the chunk minimum / best / runner-up exactly like nn_kernel, and resolve the winner.  One lane of warp 4
+// issues the MMAs; the accumulator is double-buffered in TMEM (2 x 256 columns) and the query operand in shared memory, so the
+// tensor cores work on tile t+1 while tile t is being reduced and on the next query tile during the re-check.
+constexpr int kTcM = 128, kTcK = 32;
+constexpr int kTcMaxC = 2048;                       // resident candidates per item
+constexpr uint32_t kTcLBO = 128, kTcSBO = 512;      // bytes between the K chunks of 8 rows / between groups of 8 rows
+constexpr size_t kTcSmemB = (size_t)(kTcMaxC + 128) * kTcK * 2;    // 128 KB (+ tile padding) operand image of the candidates
+constexpr size_t kTcSmemC = (size_t)3 * kTcMaxC * sizeof(float);   // 24 KB X|Y|Z
+constexpr size_t kTcSmemA = (size_t)2 * kTcM * kTcK * 2;           // 16 KB, two query tiles
+constexpr int kTcMaxGroup = 16;                     // query tiles per work item at most (their running results live in shared memory)
+constexpr size_t kTcSmemR = (size_t)kTcMaxGroup * kTcM * 8;        // 16 KB running (distance, index) per query of the group
+constexpr size_t kTcSmem = kTcSmemB + kTcSmemC + kTcSmemA + kTcSmemR;
+
+struct TCParams {
+    NNParams nn;      // clouds, images, outputs, sizes, lengths (the split fields are unused)
+    int groups[2];    // query groups per pair for direction 0 / 1
+    int gtiles;       // query tiles (128 queries) per group
+    int items;        // B * (groups[0] + groups[1])
+};
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// a wait that cannot hang the GPU: a protocol bug traps (the launch fails) instead of spinning forever
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (unsigned spins = 0; !done; spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done && spins > (1u << 24)) __trap();   // try_wait itself blocks for a while; 2^24 polls is many seconds
+    }
+}
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
+    // start address, leading (K chunk) and stride (8-row group) byte offsets in 16-byte units; version 1 (sm_100); no swizzle
+    return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)(kTcLBO >> 4) << 16) | ((uint64_t)(kTcSBO >> 4) << 32) | ((uint64_t)1 << 46);
+}
+// x = p1 + p2 + p3 exactly (three bf16 values, returned as their 16-bit patterns)
+__device__ __forceinline__ void bf16_split3(float x, uint32_t &p1, uint32_t &p2, uint32_t &p3) {
+    uint32_t h;
+    asm("{\n\t.reg .b16 t;\n\tcvt.rn.bf16.f32 t, %1;\n\tmov.b32 %0, {t, t};\n\t}" : "=r"(h) : "f"(x));
+    p1 = h & 0xffffu;
+    const float r1 = __fsub_rn(x, __uint_as_float(p1 << 16));
+    asm("{\n\t.reg .b16 t;\n\tcvt.rn.bf16.f32 t, %1;\n\tmov.b32 %0, {t, t};\n\t}" : "=r"(h) : "f"(r1));
+    p2 = h & 0xffffu;
+    const float r2 = __fsub_rn(r1, __uint_as_float(p2 << 16));
+    asm("{\n\t.reg .b16 t;\n\tcvt.rn.bf16.f32 t, %1;\n\tmov.b32 %0, {t, t};\n\t}" : "=r"(h) : "f"(r2));
+    p3 = h & 0xffffu;
+}
+// one operand row (32 bf16 = four 16-byte K chunks) of the canonical layout: row r of a tile starting at `base`
+__device__ __forceinline__ unsigned char *tc_row(unsigned char *base, int r) { return base + (size_t)(r >> 3) * kTcSBO + (size_t)(r & 7) * 16; }
+// candidate row: per coordinate [b1 b2 b1 b3 b2 b1 b3 b2], then [w1 w2 w3 0 0 0 0 0]
+__device__ __forceinline__ void tc_write_candidate(unsigned char *row, float x, float y, float z, float w) {
+    const float c[3] = {x, y, z};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        uint32_t b1, b2, b3;
+        bf16_split3(c[d], b1, b2, b3);
+        *reinterpret_cast<uint4 *>(row + d * kTcLBO) = make_uint4(b1 | (b2 << 16), b1 | (b3 << 16), b2 | (b1 << 16), b3 | (b2 << 16));
+    }
+    uint32_t w1, w2, w3;
+    bf16_split3(w, w1, w2, w3);
+    *reinterpret_cast<uint4 *>(row + 3 * kTcLBO) = make_uint4(w1 | (w2 << 16), w3, 0u, 0u);
+}
+// query row: per coordinate the pieces of -2 q_d as [a1 a1 a2 a1 a2 a3 a2 a3], then [1 1 1 0 0 0 0 0]
+__device__ __forceinline__ void tc_write_query(unsigned char *row, float x, float y, float z) {
+    const float q[3] = {-2.0f * x, -2.0f * y, -2.0f * z};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        uint32_t a1, a2, a3;
+        bf16_split3(q[d], a1, a2, a3);
+        *reinterpret_cast<uint4 *>(row + d * kTcLBO) = make_uint4(a1 | (a1 << 16), a2 | (a1 << 16), a2 | (a3 << 16), a2 | (a3 << 16));
+    }
+    *reinterpret_cast<uint4 *>(row + 3 * kTcLBO) = make_uint4(0x3f803f80u, 0x3f80u, 0u, 0u);
+}
+__device__ __forceinline__ float min32(const uint32_t (&v)[32]) {
+    float t[11];
+#pragma unroll
+    for (int i = 0; i < 10; i++) t[i] = fminf(fminf(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1])), __uint_as_float(v[3 * i + 2]));
+    t[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    const float u0 = fminf(fminf(t[0], t[1]), t[2]), u1 = fminf(fminf(t[3], t[4]), t[5]), u2 = fminf(fminf(t[6], t[7]), t[8]);
+    return fminf(fminf(fminf(u0, u1), u2), fminf(t[9], t[10]));
+}
+#define URED_TMEM_LD32(v, taddr)                                                                                                      \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, " \
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                                 \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),       \
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),            \
+                   "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),           \
+                   "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                         \
+                 : "r"(taddr)                                                                                                        \
+                 : "memory")
+
+#ifdef URED_TC_PROFILE
+__device__ long long g_tc_prof[16];   // [0] items [1] build [2] wait full [3] tmem read + reduce [4] merge + re-check [5] total  (thread 0 of CTA 0)
+#define TC_T(x) const long long x = clock64()
+#define TC_ADD(i, a, b) do { if (blockIdx.x == 0 && tid == 0) g_tc_prof[i] += (b) - (a); } while (0)
+#else
+#define TC_T(x)
+#define TC_ADD(i, a, b)
+#endif
+// NSETS sets of four query warps take the accumulator tiles in turn (tile counter % NSETS); NACC accumulators of N columns each
+// form the ring the MMA warp fills (NACC * N <= 512 TMEM columns).
+// SPLIT: every set reads every tile, set s the columns [s N / NSETS, (s + 1) N / NSETS) -- the tensor core then refills one
+// accumulator while ALL query warps drain the other, instead of each set waiting out the refill of its own.
+template <int NSETS, int NACC, int N, bool SPLIT>
+__global__ void __launch_bounds__(32 * (4 * NSETS + 5), 1) nn_tc_kernel(const TCParams tp) {
+    constexpr int kChunksPerSet = SPLIT ? N / 32 / NSETS : N / 32;
+    static_assert(!SPLIT || (N / 32) % NSETS == 0, "SPLIT: the tile's chunks must divide among the sets");
+    constexpr int kTcN = N, kTcAcc = NACC, kTcThreads = 32 * (4 * NSETS + 5);
+    constexpr int kQueryWarps = 4 * NSETS;
+    static_assert(NACC * N <= 512 && N % 32 == 0 && N <= 256, "accumulator ring must fit the 512 TMEM columns");
+    const NNParams &p = tp.nn;
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    unsigned char *Bimg = tc_smem;
+    float *Cx = reinterpret_cast<float *>(tc_smem + kTcSmemB), *Cy = Cx + kTcMaxC, *Cz = Cy + kTcMaxC;
+    unsigned char *Abuf = tc_smem + kTcSmemB + kTcSmemC;
+    float *run_d = reinterpret_cast<float *>(tc_smem + kTcSmemB + kTcSmemC + kTcSmemA);   // clouds of more than kTcMaxC candidates:
+    int *run_i = reinterpret_cast<int *>(run_d + kTcMaxGroup * kTcM);                     // best so far over the candidate ranges
+    __shared__ __align__(8) uint64_t full_bar[kTcAcc], empty_bar[kTcAcc], a_bar[2], r_bar[2], done_bar[2], c_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float x_best[2][NSETS][kTcM], x_second[2][NSETS][kTcM];   // [query-tile parity][set][query]: the sets' partial results
+    __shared__ int x_chunk[2][NSETS][kTcM];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warps [0, 4 NSETS): query warps, set = warp / 4 (warp w reads TMEM lanes 32 (w % 4) ..); then the MMA warp; then 4 resolver warps
+    const bool is_query_thread = warp < kQueryWarps, is_mma_thread = tid == 32 * kQueryWarps, is_resolver = warp > kQueryWarps;
+    const int set = warp >> 2;
+    const int t = is_resolver ? tid - 32 * (kQueryWarps + 1) : (tid & (kTcM - 1));   // the query of the tile this thread looks after
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kTcAcc; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], SPLIT ? NSETS * kTcM : kTcM); }
+#pragma unroll
+        for (int i = 0; i < 2; i++) { mbar_init(&a_bar[i], kTcM); mbar_init(&r_bar[i], NSETS * kTcM); mbar_init(&done_bar[i], kTcM); }
+        mbar_init(&c_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    // kind::f16 instruction descriptor: fp32 accumulator, bf16 x bf16, both operands K-major, N / 8 at bit 17, M / 16 at bit 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+
+    uint32_t tile_ctr = 0, qt_ctr = 0, item_ctr = 0;   // accumulator tiles / query tiles / (item, range) passes this CTA has gone through (all threads agree)
+    const int per_pair = tp.groups[0] + tp.groups[1];
+    for (int item = blockIdx.x; item < tp.items; item += gridDim.x) {
+        const int b = item / per_pair;
+        const int rem = item - b * per_pair;
+        const int dir = rem >= tp.groups[0] ? 1 : 0;
+        const int grp = dir ? rem - tp.groups[0] : rem;
+        const int c1 = b / p.rep1, c2 = b % p.mod2;
+        const int cq = dir ? c2 : c1, cc = dir ? c1 : c2;
+        const int nq = dir ? p.n[1] : p.n[0];
+        const int ncp_max = dir ? p.np[0] : p.np[1];
+        const int *len_q = dir ? p.len[1] : p.len[0], *len_c = dir ? p.len[0] : p.len[1];
+        const int nq_v = len_q ? max(0, min(len_q[cq], nq)) : nq;
+        const int nc_all = len_c ? max(0, min(len_c[cc], dir ? p.n[0] : p.n[1])) : (dir ? p.n[0] : p.n[1]);
+        const float *__restrict__ qxyz = (dir ? p.xyz[1] : p.xyz[0]) + (size_t)cq * nq * 3;
+        const int nqp_max = dir ? p.np[1] : p.np[0];
+        const float *__restrict__ qsoa = (dir ? p.soa[1] : p.soa[0]);
+        if (qsoa) qsoa += (size_t)cq * ((size_t)nqp_max * 4 + kPackTail);
+        const float *__restrict__ csoa = (dir ? p.soa[0] : p.soa[1]) + (size_t)cc * ((size_t)ncp_max * 4 + kPackTail);
+        float *out_d = (dir ? p.dist[1] : p.dist[0]) + (size_t)b * nq;
+        int *out_i = (dir ? p.idx[1] : p.idx[0]) + (size_t)b * nq;
+        const int qt_lo = grp * tp.gtiles;
+        const int qt_all = (nq + kTcM - 1) / kTcM;                       // tiles that have outputs to write
+        const int qt_hi = min(qt_lo + tp.gtiles, qt_all);
+        const int qt_search = nc_all > 0 ? min(qt_hi, (nq_v + kTcM - 1) / kTcM) : qt_lo;   // tiles [qt_lo, qt_search) hold valid queries
+        // Clouds of more than kTcMaxC candidates are scanned range by range (ascending); every range is resolved exactly and
+        // a strict '<' against the running result keeps the lowest index among equal distances (chamfer3D.cu:126's rule).
+        const int nranges = qt_search > qt_lo ? (nc_all + kTcMaxC - 1) / kTcMaxC : 1;
+        auto load_query = [&](int qt, float &x, float &y, float &z) {
+            int j = qt * kTcM + t;
+            j = j < nq_v ? j : nq_v - 1;
+            if (qsoa) { x = qsoa[j]; y = qsoa[nqp_max + j]; z = qsoa[2 * nqp_max + j]; }
+            else { x = qxyz[j * 3 + 0]; y = qxyz[j * 3 + 1]; z = qxyz[j * 3 + 2]; }
+        };
+      for (int rng = 0; rng < nranges; rng++) {
+        const int k_lo = rng * kTcMaxC;
+        const int nc = min(nc_all - k_lo, kTcMaxC);
+        const int ncp = (nc + kChunk - 1) / kChunk * kChunk;
+        const int ntiles = (ncp + kTcN - 1) / kTcN;
+        const bool first_range = rng == 0, last_range = rng == nranges - 1;
+
+        __syncthreads();   // the previous pass is finished everywhere: its operand image and X|Y|Z may be overwritten
+        TC_T(t_item);
+        if (qt_search > qt_lo) {
+            if (tid == 0) {
+                const uint32_t bytes = (uint32_t)ncp * sizeof(float);
+                mbar_arrive_expect_tx(&c_bar, 3 * bytes);
+                tma_bulk_g2s(Cx, csoa + k_lo, bytes, &c_bar);
+                tma_bulk_g2s(Cy, csoa + ncp_max + k_lo, bytes, &c_bar);
+                tma_bulk_g2s(Cz, csoa + 2 * (size_t)ncp_max + k_lo, bytes, &c_bar);
+            }
+            // operand image of the candidates; rows past the padded cloud can never win (W = 3e38, coordinates 0)
+#pragma unroll 2
+            for (int r = tid; r < ntiles * kTcN; r += kTcThreads) {
+                unsigned char *row = tc_row(Bimg, r);
+                if (r < ncp) tc_write_candidate(row, csoa[k_lo + r], csoa[ncp_max + k_lo + r], csoa[2 * (size_t)ncp_max + k_lo + r], csoa[3 * (size_t)ncp_max + k_lo + r]);
+                else tc_write_candidate(row, 0.0f, 0.0f, 0.0f, 3.0e38f);
+            }
+            if (is_resolver) {   // operand rows of the first two query tiles (the later ones follow during the pass)
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+                    if (qt_lo + i < qt_search) {
+                        float x, y, z;
+                        load_query(qt_lo + i, x, y, z);
+                        tc_write_query(tc_row(Abuf + ((qt_ctr + i) & 1) * (kTcSmemA / 2), t), x, y, z);
+                    }
+            }
+            fence_proxy_async();   // generic-proxy writes of this thread -> visible to the tensor core's (async proxy) reads
+            if (is_resolver) {
+                mbar_arrive(&a_bar[qt_ctr & 1]);
+                if (qt_lo + 1 < qt_search) mbar_arrive(&a_bar[(qt_ctr + 1) & 1]);
+            }
+        }
+        __syncthreads();       // operand image complete
+        TC_T(t_built);
+        TC_ADD(1, t_item, t_built);
+        TC_ADD(0, 0, 1);
+
+        if (warp == kQueryWarps) {   // the whole warp walks the loop (it stays converged for the block barriers); lane 0 issues
+            uint32_t tc = tile_ctr, qc = qt_ctr;
+            for (int qt = qt_lo; qt < qt_search; qt++, qc++) {
+                mbar_wait_bounded(&a_bar[qc & 1], (qc >> 1) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(Abuf + (qc & 1) * (kTcSmemA / 2));
+                for (int j = 0; j < ntiles; j++, tc++) {
+                    const uint32_t acc = tc % kTcAcc, use = tc / kTcAcc;
+                    if (use > 0) { mbar_wait_bounded(&empty_bar[acc], (use - 1) & 1); tc_fence_after(); }
+                    if (is_mma_thread) {
+                        const uint32_t b_addr = smem_u32(Bimg) + (uint32_t)j * (kTcN * kTcK * 2);
+#pragma unroll
+                        for (int k = 0; k < kTcK / 16; k++) {
+                            const uint64_t da = tc_smem_desc(a_addr + k * 2 * kTcLBO), db = tc_smem_desc(b_addr + k * 2 * kTcLBO);
+                            const uint32_t accumulate = k > 0;
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                         ::"r"(tmem + acc * kTcN), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+                        }
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&full_bar[acc])) : "memory");
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (is_query_thread) {
+            // The sets take the tiles in turn, so one set's barrier waits and fences overlap another's TMEM reads.  The partial
+            // (best, runner-up, chunk) triples go to the resolvers through shared memory.
+            uint32_t tc = tile_ctr, qc = qt_ctr;
+            for (int qt = qt_lo; qt < qt_search; qt++, qc++) {
+                float best = kInf, second = kInf;
+                int bchunk = 0;
+                for (int j = 0; j < ntiles; j++, tc++) {
+                    if (!SPLIT && (int)(tc % NSETS) != set) continue;
+                    const uint32_t acc = tc % kTcAcc, use = tc / kTcAcc;
+                    TC_T(t_w0);
+                    mbar_wait_bounded(&full_bar[acc], use & 1);
+                    tc_fence_after();
+                    TC_T(t_w1);
+                    TC_ADD(2, t_w0, t_w1);
+                    const int c_lo = SPLIT ? set * kChunksPerSet : 0;
+                    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + acc * kTcN + c_lo * 32;
+                    uint32_t va[32], vb[32];
+                    URED_TMEM_LD32(va, taddr);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < kChunksPerSet; c++) {
+                        // chunk c is in registers; chunk c+1 is requested before c is reduced
+                        if (c + 1 < kChunksPerSet) {
+                            if (c & 1) URED_TMEM_LD32(va, taddr + (c + 1) * 32); else URED_TMEM_LD32(vb, taddr + (c + 1) * 32);
+                        }
+                        const float cm = (c & 1) ? min32(vb) : min32(va);
+                        const int chunk_id = j * kTcN + (c_lo + c) * 32;
+                        const bool better = cm < best;      // strict '<' in ascending chunk order keeps the FIRST chunk holding the minimum
+                        second = fminf(second, fmaxf(cm, best));
+                        best = fminf(best, cm);
+                        bchunk = better ? chunk_id : bchunk;
+                        if (c + 1 < kChunksPerSet) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&empty_bar[acc]);
+                    TC_T(t_w2);
+                    TC_ADD(3, t_w1, t_w2);
+                }
+                TC_T(t_r0);
+                const int slot = qc & 1;
+                const uint32_t suse = qc >> 1;
+                if (suse > 0) mbar_wait_bounded(&done_bar[slot], (suse - 1) & 1);   // the resolvers have read the slot's previous contents
+                x_best[slot][set][t] = best; x_second[slot][set][t] = second; x_chunk[slot][set][t] = bchunk;
+                mbar_arrive(&r_bar[slot]);
+                TC_T(t_r1);
+                TC_ADD(4, t_r0, t_r1);
+            }
+            TC_T(t_end);
+            TC_ADD(5, t_item, t_end);
+        }
+        if (is_resolver) {
+            // One thread per query of the tile: merge the two sets' triples, resolve the winning chunk exactly (nn_kernel's
+            // re-check, from the resident X|Y|Z), rescan ambiguous queries, write the result -- off the TMEM readers' path.
+            const float cn = __fsqrt_ru(csoa[(size_t)ncp_max * 4]) * 1.000001f;   // max |c| of the candidate cloud (block tail)
+            const int rot = lane & 7;
+            uint32_t qc = qt_ctr;
+            bool c_ready = false;
+            for (int qt = qt_lo; qt < qt_search; qt++, qc++) {
+                float qx, qy, qz, fx = 0.0f, fy = 0.0f, fz = 0.0f;
+                load_query(qt, qx, qy, qz);
+                const bool feed = qt + 2 < qt_search;
+                if (feed) load_query(qt + 2, fx, fy, fz);
+                const int slot = qc & 1;
+                mbar_wait_bounded(&r_bar[slot], (qc >> 1) & 1);
+                float best = x_best[slot][0][t], second = x_second[slot][0][t];
+                int bchunk = x_chunk[slot][0][t];
+#pragma unroll
+                for (int o = 1; o < NSETS; o++) {
+                    const float ob = x_best[slot][o][t], os = x_second[slot][o][t];
+                    const int oc = x_chunk[slot][o][t];
+                    second = fminf(fminf(second, os), fmaxf(best, ob));
+                    if (ob < best || (ob == best && oc < bchunk)) bchunk = oc;   // the FIRST chunk holding the minimum
+                    best = fminf(best, ob);
+                }
+                mbar_arrive(&done_bar[slot]);
+                if (feed) {   // every tile of query tile qt has been reduced, so its MMAs -- the last readers of this operand buffer -- are complete
+                    tc_write_query(tc_row(Abuf + (qc & 1) * (kTcSmemA / 2), t), fx, fy, fz);
+                    fence_proxy_async();
+                    mbar_arrive(&a_bar[qc & 1]);
+                }
+                if (!c_ready) { mbar_wait_bounded(&c_bar, item_ctr & 1); c_ready = true; }
+                const int c = min(bchunk, ncp - kChunk);
+                const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
+                unsigned bdu = 0u, hdu = 0u;
+                int bi = c;
+                const float *sX = Cx + c, *sY = Cy + c, *sZ = Cz + c;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int piece = (k + rot) & 7;
+                    if (k > 0 && piece == 0) { hdu = bdu; bdu += 1u; }
+                    const float4 x4 = *reinterpret_cast<const float4 *>(sX + piece * 4);
+                    const float4 y4 = *reinterpret_cast<const float4 *>(sY + piece * 4);
+                    const float4 z4 = *reinterpret_cast<const float4 *>(sZ + piece * 4);
+                    const float2 dx0 = __fadd2_rn(make_float2(x4.x, x4.y), nqx), dx1 = __fadd2_rn(make_float2(x4.z, x4.w), nqx);
+                    const float2 dy0 = __fadd2_rn(make_float2(y4.x, y4.y), nqy), dy1 = __fadd2_rn(make_float2(y4.z, y4.w), nqy);
+                    const float2 dz0 = __fadd2_rn(make_float2(z4.x, z4.y), nqz), dz1 = __fadd2_rn(make_float2(z4.z, z4.w), nqz);
+                    const float2 d0 = __ffma2_rn(dz0, dz0, __ffma2_rn(dx0, dx0, __fmul2_rn(dy0, dy0)));
+                    const float2 d1 = __ffma2_rn(dz1, dz1, __ffma2_rn(dx1, dx1, __fmul2_rn(dy1, dy1)));
+                    const int i0 = c + piece * 4;
+                    const unsigned u0 = __float_as_uint(d0.x), u1 = __float_as_uint(d0.y), u2 = __float_as_uint(d1.x), u3 = __float_as_uint(d1.y);
+                    if (k == 0 || u0 < bdu) { bdu = u0; bi = i0; }
+                    if (u1 < bdu) { bdu = u1; bi = i0 + 1; }
+                    if (u2 < bdu) { bdu = u2; bi = i0 + 2; }
+                    if (u3 < bdu) { bdu = u3; bi = i0 + 3; }
+                }
+                if (rot != 0 && bi >= c + rot * 4) bdu = hdu;  // the winner predates the wrap: undo the bump
+                float bd = __uint_as_float(bdu);
+                {
+                    const float qn = __fsqrt_ru(__fmaf_rn(qz, qz, __fmaf_rn(qy, qy, qx * qx))) * 1.000001f;
+                    const float S = qn + cn;
+                    const float eps = __fmaf_rn(S * S, 1.9073486e-6f /* 2^-19 */, 1e-35f);
+                    const bool ambiguous = !(second > best + eps);
+                    unsigned todo = __ballot_sync(0xffffffffu, ambiguous);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const float ax = __shfl_sync(0xffffffffu, qx, src), ay = __shfl_sync(0xffffffffu, qy, src), az = __shfl_sync(0xffffffffu, qz, src);
+                        float wd = kInf;
+                        int wi = 0x7fffffff;
+                        for (int k = lane; k < nc; k += 32) {
+                            const float d = exact_d(Cx[k], Cy[k], Cz[k], ax, ay, az);
+                            if (d < wd || wi == 0x7fffffff) { wd = d; wi = k; }
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float od = __shfl_xor_sync(0xffffffffu, wd, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                            if (oi != 0x7fffffff && (wi == 0x7fffffff || od < wd || (od == wd && oi < wi))) { wd = od; wi = oi; }
+                        }
+                        if (lane == src) { bd = wd; bi = wi; }
+                    }
+                }
+                bi += k_lo;
+                const int slot_r = (qt - qt_lo) * kTcM + t;
+                if (!first_range) {
+                    const float rd = run_d[slot_r];
+                    if (!(bd < rd)) { bd = rd; bi = run_i[slot_r]; }
+                }
+                if (!last_range) { run_d[slot_r] = bd; run_i[slot_r] = bi; }
+                const int j = qt * kTcM + t;
+                if (last_range && j < nq) {
+                    if (j >= nq_v) { bd = 0.0f; bi = 0; }   // past the valid length of a ragged cloud
+                    out_d[j] = bd;
+                    out_i[j] = bi;
+                }
+            }
+            // tiles without a valid query (or an empty candidate cloud): the reference leaves its zero-filled outputs untouched
+            if (last_range)
+                for (int qt = qt_search; qt < qt_hi; qt++) {
+                    const int j = qt * kTcM + t;
+                    if (j < nq) { out_d[j] = 0.0f; out_i[j] = 0; }
+                }
+        }
+        const uint32_t did = (uint32_t)max(qt_search - qt_lo, 0);
+        tile_ctr += did * (uint32_t)ntiles;
+        qt_ctr += did;
+        item_ctr += did ? 1u : 0u;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
 // Launch shape: a kernel variant (T threads x R queries per thread, MINB resident CTAs per SM) and nsplit candidate
 // splits.  Measured on B200 (profiles/r02_sweep_nn*.jsonl: every variant x split count on the BASELINE shapes):
 //   * the 4-query, 128-thread shape wins whenever there are enough query tiles to give every SM two CTAs; fatter
@@ -1812,6 +2253,18 @@ inline int count2_of(int B, int mod2) { return B < mod2 ? B : mod2; }
 
 inline bool flags_env_general() { return env_int("URED_GRAD_GENERAL", 0) != 0; }  // tests: force the global-atomic backward
 
+// nn_tc_kernel: query tiles per work item.  A whole cloud per item amortises the operand image best (built once per item);
+// smaller groups when the batch would otherwise leave SMs without work.
+inline int tc_group_tiles(int B, int t1, int t2) {
+    const int forced = env_int("URED_TC_GTILES", 0);
+    if (forced > 0) return forced < kTcMaxGroup ? forced : kTcMaxGroup;
+    const int tmax = t1 > t2 ? t1 : t2;
+    int g = 1;
+    while (g < tmax && g < kTcMaxGroup) g <<= 1;
+    while (g > 1 && (long long)B * ((t1 + g - 1) / g + (t2 + g - 1) / g) < 3ll * 148) g >>= 1;
+    return g;
+}
+
 template <bool SCREEN, int R, int T, int MINB, bool PF = false>
 int launch_nn(const NNParams &p, int B, cudaStream_t st) {
     constexpr int NARR = SCREEN ? 4 : 3;
@@ -1848,6 +2301,15 @@ int launch_nn_variant(int variant, bool exact, const NNParams &p, int B, cudaStr
 extern "C" {
 
 int ured_abi_version(void) { return URED_ABI_VERSION; }
+#ifdef URED_TC_PROFILE
+// development build only (-DURED_TC_PROFILE): read and clear nn_tc_kernel's phase counters
+int ured_debug_tc_profile(long long *out16) {
+    long long zero[16] = {0};
+    cudaMemcpyFromSymbol(out16, g_tc_prof, sizeof(zero));
+    cudaMemcpyToSymbol(g_tc_prof, zero, sizeof(zero));
+    return 0;
+}
+#endif
 const char *ured_last_error_string(void) { return g_err; }
 unsigned long long ured_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -1928,9 +2390,40 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
     p.rep1 = rep1; p.mod2 = mod2;
     p.len[0] = len1; p.len[1] = len2;
     const bool exact = (flags & URED_FLAG_EXACT_ONLY) != 0;
+    const bool one_dir = (flags & URED_FLAG_ONE_DIRECTION) != 0;  // only cloud-1 points search cloud 2 (K=1 kNN)
+    // screening on the tensor cores: every candidate cloud of the call fits the resident operand image
+    if (!exact && env_int("URED_NN_TC", 1)) {
+        TCParams tp;
+        tp.nn = p;
+        tp.nn.qtiles[0] = tp.nn.qtiles[1] = 0; tp.nn.nsplit = 1; tp.nn.full_items = tp.nn.split_items = 0;
+        tp.nn.part_dist = nullptr; tp.nn.part_idx = nullptr;
+        const int t1 = (n1 + kTcM - 1) / kTcM, t2 = one_dir ? 0 : (n2 + kTcM - 1) / kTcM;
+        tp.gtiles = tc_group_tiles(B, t1, t2);
+        tp.groups[0] = (t1 + tp.gtiles - 1) / tp.gtiles;
+        tp.groups[1] = (t2 + tp.gtiles - 1) / tp.gtiles;
+        const long long items = (long long)B * (tp.groups[0] + tp.groups[1]);
+        if (items > 0x7fffffffll) return fail_arg(URED_E_SHAPE, "too many work items for one launch");
+        tp.items = (int)items;
+        const int grid = (int)(items < 148 ? items : 148);   // one persistent CTA per SM (B200: 148)
+        const int cfg = env_int("URED_TC_CONFIG", 0);
+#define URED_TC_LAUNCH(NSETS, NACC, N, SPLIT)                                                                                           \
+    do {                                                                                                                                \
+        URED_CUDA(cudaFuncSetAttribute(nn_tc_kernel<NSETS, NACC, N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem), "nn_tc smem attribute"); \
+        nn_tc_kernel<NSETS, NACC, N, SPLIT><<<grid, 32 * (4 * NSETS + 5), kTcSmem, st>>>(tp);                                           \
+    } while (0)
+        switch (cfg) {
+            case 1: URED_TC_LAUNCH(1, 2, 256, false); break;
+            case 2: URED_TC_LAUNCH(2, 2, 256, true); break;
+            case 3: URED_TC_LAUNCH(4, 2, 256, true); break;
+            case 4: URED_TC_LAUNCH(2, 3, 128, true); break;
+            default: URED_TC_LAUNCH(2, 2, 256, false); break;
+        }
+#undef URED_TC_LAUNCH
+        URED_COUNT_LAUNCH();
+        return check_cuda(cudaGetLastError(), "nn_tc_kernel launch");
+    }
     const NNShape sh = choose_nn_shape(B, n1, n2, exact);
     const int QT = sh.R * sh.T;
-    const bool one_dir = (flags & URED_FLAG_ONE_DIRECTION) != 0;  // only cloud-1 points search cloud 2 (K=1 kNN)
     p.qtiles[0] = (n1 + QT - 1) / QT;
     p.qtiles[1] = one_dir ? 0 : (n2 + QT - 1) / QT;
     const long long items = (long long)B * (p.qtiles[0] + p.qtiles[1]);
