@@ -24,6 +24,7 @@ NVCC_FLAGS = [
 URED_FLAG_EXACT_ONLY = 1
 URED_FLAG_NON_REG = 2
 URED_FLAG_ONE_DIRECTION = 4
+URED_FLAG_FP32_SCREEN = 8
 
 _i, _u, _f, _p, _sz = ctypes.c_int, ctypes.c_uint, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 _SIGNATURES = {

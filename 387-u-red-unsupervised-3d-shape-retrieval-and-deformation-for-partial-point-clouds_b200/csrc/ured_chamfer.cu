@@ -576,6 +576,8 @@ __global__ void __launch_bounds__(256) merge_splits_kernel(const MergeParams m) 
 // issues the MMAs; the accumulator is double-buffered in TMEM (2 x 256 columns) and the query operand in shared memory, so the
 // tensor cores work on tile t+1 while tile t is being reduced and on the next query tile during the re-check.
 constexpr int kTcM = 128, kTcK = 32;
+constexpr int kTcDefaultSets = 2;                                  // query-warp sets of the default configuration
+constexpr int kTcLaunchThreads = 32 * (5 * kTcDefaultSets + 4);    // query warps + one MMA warp per set + 4 resolver warps
 constexpr int kTcMaxC = 2048;                       // resident candidates per item
 constexpr uint32_t kTcLBO = 128, kTcSBO = 512;      // bytes between the K chunks of 8 rows / between groups of 8 rows
 constexpr size_t kTcSmemB = (size_t)(kTcMaxC + 128) * kTcK * 2;    // 128 KB (+ tile padding) operand image of the candidates
@@ -675,8 +677,14 @@ __device__ __forceinline__ float min32(const uint32_t (&v)[32]) {
 #ifdef URED_TC_PROFILE
 __device__ long long g_tc_prof[16];   // [0] items [1] build [2] wait full [3] tmem read + reduce [4] merge + re-check [5] total  (thread 0 of CTA 0)
 #define TC_T(x) const long long x = clock64()
-#define TC_ADD(i, a, b) do { if (blockIdx.x == 0 && tid == 0) g_tc_prof[i] += (b) - (a); } while (0)
+#define TC_ADD(i, a, b) do { if (tid == 0) pacc[i] += (b) - (a); } while (0)            // (registers: a global update here would stall the thread)
+#define TC_ADDM(i, a, b) do { if (is_mma_thread && mma_id == 0) pacc[i] += (b) - (a); } while (0)
+#define TC_PROF_DECL long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define TC_PROF_FLUSH do { if (blockIdx.x == 0 && (tid == 0 || (is_mma_thread && mma_id == 0))) for (int i_ = 0; i_ < 10; i_++) atomicAdd((unsigned long long *)&g_tc_prof[i_], (unsigned long long)pacc[i_]); } while (0)
 #else
+#define TC_PROF_DECL
+#define TC_PROF_FLUSH
+#define TC_ADDM(i, a, b)
 #define TC_T(x)
 #define TC_ADD(i, a, b)
 #endif
@@ -684,11 +692,14 @@ __device__ long long g_tc_prof[16];   // [0] items [1] build [2] wait full [3] t
 // form the ring the MMA warp fills (NACC * N <= 512 TMEM columns).
 // SPLIT: every set reads every tile, set s the columns [s N / NSETS, (s + 1) N / NSETS) -- the tensor core then refills one
 // accumulator while ALL query warps drain the other, instead of each set waiting out the refill of its own.
+// One MMA-issuing warp per set (non-SPLIT): issuing a tile's two MMAs and the commit costs the issuing thread ~300 cycles
+// whatever the tile width (measured), so one warp feeding every accumulator in turn paces the whole CTA.
 template <int NSETS, int NACC, int N, bool SPLIT>
-__global__ void __launch_bounds__(32 * (4 * NSETS + 5), 1) nn_tc_kernel(const TCParams tp) {
+__global__ void __launch_bounds__(32 * (4 * NSETS + (SPLIT ? 1 : NSETS) + 4), 1) nn_tc_kernel(const TCParams tp) {
+    constexpr int kMmaWarps = SPLIT ? 1 : NSETS;
     constexpr int kChunksPerSet = SPLIT ? N / 32 / NSETS : N / 32;
     static_assert(!SPLIT || (N / 32) % NSETS == 0, "SPLIT: the tile's chunks must divide among the sets");
-    constexpr int kTcN = N, kTcAcc = NACC, kTcThreads = 32 * (4 * NSETS + 5);
+    constexpr int kTcN = N, kTcAcc = NACC, kTcThreads = 32 * (4 * NSETS + kMmaWarps + 4);
     constexpr int kQueryWarps = 4 * NSETS;
     static_assert(NACC * N <= 512 && N % 32 == 0 && N <= 256, "accumulator ring must fit the 512 TMEM columns");
     const NNParams &p = tp.nn;
@@ -704,9 +715,11 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + 5), 1) nn_tc_kernel(const TC
     __shared__ int x_chunk[2][NSETS][kTcM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // warps [0, 4 NSETS): query warps, set = warp / 4 (warp w reads TMEM lanes 32 (w % 4) ..); then the MMA warp; then 4 resolver warps
-    const bool is_query_thread = warp < kQueryWarps, is_mma_thread = tid == 32 * kQueryWarps, is_resolver = warp > kQueryWarps;
+    const bool is_query_thread = warp < kQueryWarps, is_mma_warp = warp >= kQueryWarps && warp < kQueryWarps + kMmaWarps;
+    const bool is_mma_thread = is_mma_warp && lane == 0, is_resolver = warp >= kQueryWarps + kMmaWarps;
     const int set = warp >> 2;
-    const int t = is_resolver ? tid - 32 * (kQueryWarps + 1) : (tid & (kTcM - 1));   // the query of the tile this thread looks after
+    const int mma_id = warp - kQueryWarps;   // MMA warp m issues the tiles of set m
+    const int t = is_resolver ? tid - 32 * (kQueryWarps + kMmaWarps) : (tid & (kTcM - 1));   // the query of the tile this thread looks after
 
     if (tid == 0) {
 #pragma unroll
@@ -727,6 +740,7 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + 5), 1) nn_tc_kernel(const TC
     // kind::f16 instruction descriptor: fp32 accumulator, bf16 x bf16, both operands K-major, N / 8 at bit 17, M / 16 at bit 24
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
 
+    TC_PROF_DECL;
     uint32_t tile_ctr = 0, qt_ctr = 0, item_ctr = 0;   // accumulator tiles / query tiles / (item, range) passes this CTA has gone through (all threads agree)
     const int per_pair = tp.groups[0] + tp.groups[1];
     for (int item = blockIdx.x; item < tp.items; item += gridDim.x) {
@@ -805,15 +819,22 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + 5), 1) nn_tc_kernel(const TC
         TC_ADD(1, t_item, t_built);
         TC_ADD(0, 0, 1);
 
-        if (warp == kQueryWarps) {   // the whole warp walks the loop (it stays converged for the block barriers); lane 0 issues
+        if (is_mma_warp) {   // the whole warp walks the loop (it stays converged for the block barriers); lane 0 issues
             uint32_t tc = tile_ctr, qc = qt_ctr;
             for (int qt = qt_lo; qt < qt_search; qt++, qc++) {
                 mbar_wait_bounded(&a_bar[qc & 1], (qc >> 1) & 1);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(Abuf + (qc & 1) * (kTcSmemA / 2));
                 for (int j = 0; j < ntiles; j++, tc++) {
+                    if (kMmaWarps > 1 && (int)(tc % kMmaWarps) != mma_id) continue;
                     const uint32_t acc = tc % kTcAcc, use = tc / kTcAcc;
-                    if (use > 0) { mbar_wait_bounded(&empty_bar[acc], (use - 1) & 1); tc_fence_after(); }
+                    TC_T(t_m0);
+                    if (use > 0) mbar_wait_bounded(&empty_bar[acc], (use - 1) & 1);
+                    TC_T(t_m1);
+                    if (use > 0) tc_fence_after();
+                    TC_T(t_m2);
+                    TC_ADDM(6, t_m0, t_m1);
+                    TC_ADDM(7, t_m1, t_m2);
                     if (is_mma_thread) {
                         const uint32_t b_addr = smem_u32(Bimg) + (uint32_t)j * (kTcN * kTcK * 2);
 #pragma unroll
@@ -827,6 +848,8 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + 5), 1) nn_tc_kernel(const TC
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&full_bar[acc])) : "memory");
                     }
                     __syncwarp();
+                    TC_T(t_m3);
+                    TC_ADDM(8, t_m2, t_m3);
                 }
             }
         }
@@ -990,6 +1013,7 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + 5), 1) nn_tc_kernel(const TC
         item_ctr += did ? 1u : 0u;
       }
     }
+    TC_PROF_FLUSH;
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
@@ -2253,16 +2277,28 @@ inline int count2_of(int B, int mod2) { return B < mod2 ? B : mod2; }
 
 inline bool flags_env_general() { return env_int("URED_GRAD_GENERAL", 0) != 0; }  // tests: force the global-atomic backward
 
-// nn_tc_kernel: query tiles per work item.  A whole cloud per item amortises the operand image best (built once per item);
-// smaller groups when the batch would otherwise leave SMs without work.
+// which kernel screens: the tensor-core one unless the caller asks for the difference form on every pair, for the FP32-pipe
+// screen (flag), or the environment switches it off (URED_NN_TC=0: A/B runs)
+inline bool nn_uses_tensor_cores(unsigned flags) {
+    return !(flags & (URED_FLAG_EXACT_ONLY | URED_FLAG_FP32_SCREEN)) && env_int("URED_NN_TC", 1) != 0;
+}
+// nn_tc_kernel: query tiles per work item.  An item costs one operand-image build plus pipeline fill / drain (about 1.05 query
+// tiles' worth of time, whatever the cloud size) and `g` query tiles; the persistent CTAs take ceil(items / 148) rounds.
+// Measured (B200): cfg1 41 / 46 / 56 / 66 us with g = 8 / 4 / 2 / 16, cfg2 0.488 / 0.534 / 0.620 ms with g = 16 / 8 / 4 --
+// the order this estimate gives.
 inline int tc_group_tiles(int B, int t1, int t2) {
     const int forced = env_int("URED_TC_GTILES", 0);
     if (forced > 0) return forced < kTcMaxGroup ? forced : kTcMaxGroup;
     const int tmax = t1 > t2 ? t1 : t2;
-    int g = 1;
-    while (g < tmax && g < kTcMaxGroup) g <<= 1;
-    while (g > 1 && (long long)B * ((t1 + g - 1) / g + (t2 + g - 1) / g) < 3ll * 148) g >>= 1;
-    return g;
+    int best_g = 1;
+    double best_cost = 0.0;
+    for (int g = 1; g <= kTcMaxGroup; g <<= 1) {
+        const long long items = (long long)B * ((t1 + g - 1) / g + (t2 + g - 1) / g);
+        const double cost = (double)((items + 147) / 148) * (1.05 + (double)(g < tmax ? g : tmax));
+        if (g == 1 || cost <= best_cost) { best_cost = cost; best_g = g; }
+        if (g >= tmax) break;
+    }
+    return best_g;
 }
 
 template <bool SCREEN, int R, int T, int MINB, bool PF = false>
@@ -2349,6 +2385,18 @@ size_t ured_nn_scratch_bytes(int B, int n1, int n2) {
 int ured_nn_launch_shape(int B, int n1, int n2, unsigned flags, int *variant, int *queries_per_cta, int *threads, int *nsplit,
                          int *items, int *split_items) {
     if (B <= 0 || n1 <= 0 || n2 <= 0) return fail_arg(URED_E_SHAPE, "ured_nn_launch_shape: empty problem");
+    if (nn_uses_tensor_cores(flags)) {
+        const int t1 = (n1 + kTcM - 1) / kTcM, t2 = (flags & URED_FLAG_ONE_DIRECTION) ? 0 : (n2 + kTcM - 1) / kTcM;
+        const int g = tc_group_tiles(B, t1, t2);
+        const int nbig = (flags & URED_FLAG_ONE_DIRECTION) ? n2 : (n1 > n2 ? n1 : n2);
+        if (variant) *variant = URED_NN_VARIANT_TENSOR;
+        if (queries_per_cta) *queries_per_cta = g * kTcM;
+        if (threads) *threads = kTcLaunchThreads;
+        if (nsplit) *nsplit = (nbig + kTcMaxC - 1) / kTcMaxC;     // candidate ranges, scanned one after the other by the same CTA
+        if (items) *items = (int)((long long)B * ((t1 + g - 1) / g + (t2 + g - 1) / g));
+        if (split_items) *split_items = 0;
+        return 0;
+    }
     const NNShape sh = choose_nn_shape(B, n1, n2, (flags & URED_FLAG_EXACT_ONLY) != 0);
     const int qt = sh.R * sh.T;
     const long long n_items = (long long)B * ((n1 + qt - 1) / qt + ((flags & URED_FLAG_ONE_DIRECTION) ? 0 : (n2 + qt - 1) / qt));
@@ -2392,7 +2440,7 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
     const bool exact = (flags & URED_FLAG_EXACT_ONLY) != 0;
     const bool one_dir = (flags & URED_FLAG_ONE_DIRECTION) != 0;  // only cloud-1 points search cloud 2 (K=1 kNN)
     // screening on the tensor cores: every candidate cloud of the call fits the resident operand image
-    if (!exact && env_int("URED_NN_TC", 1)) {
+    if (nn_uses_tensor_cores(flags)) {
         TCParams tp;
         tp.nn = p;
         tp.nn.qtiles[0] = tp.nn.qtiles[1] = 0; tp.nn.nsplit = 1; tp.nn.full_items = tp.nn.split_items = 0;
@@ -2409,13 +2457,14 @@ int ured_nn_packed(const float *xyz1, const void *packed1, int n1, const float *
 #define URED_TC_LAUNCH(NSETS, NACC, N, SPLIT)                                                                                           \
     do {                                                                                                                                \
         URED_CUDA(cudaFuncSetAttribute(nn_tc_kernel<NSETS, NACC, N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem), "nn_tc smem attribute"); \
-        nn_tc_kernel<NSETS, NACC, N, SPLIT><<<grid, 32 * (4 * NSETS + 5), kTcSmem, st>>>(tp);                                           \
+        nn_tc_kernel<NSETS, NACC, N, SPLIT><<<grid, 32 * (4 * NSETS + (SPLIT ? 1 : NSETS) + 4), kTcSmem, st>>>(tp);                     \
     } while (0)
+        // Measured on cfg2 (profiles/README.md, round 2): two sets taking the 256-column tiles in turn, one accumulator and one
+        // MMA warp each: 0.488 ms; one set, two accumulators: 0.583; both sets on every tile (column halves): 0.549; narrower
+        // tiles with more accumulators (4 x 128, 3 x 160): 0.61-0.86 -- the per-tile hand-off costs dominate.
         switch (cfg) {
             case 1: URED_TC_LAUNCH(1, 2, 256, false); break;
             case 2: URED_TC_LAUNCH(2, 2, 256, true); break;
-            case 3: URED_TC_LAUNCH(4, 2, 256, true); break;
-            case 4: URED_TC_LAUNCH(2, 3, 128, true); break;
             default: URED_TC_LAUNCH(2, 2, 256, false); break;
         }
 #undef URED_TC_LAUNCH

@@ -57,18 +57,21 @@ def _len_arg(name, t, count, device):
     return t.to(device=device, dtype=torch.int32).contiguous()
 
 
-def nn_forward(xyz1, xyz2, exact_only=None, len1=None, len2=None):
+def nn_forward(xyz1, xyz2, exact_only=None, len1=None, len2=None, fp32_screen=None):
     """Raw forward: (dist1, dist2, idx1, idx2) for contiguous float32 CUDA clouds.
 
     ``len1`` / ``len2`` (optional int tensors [B], may live on the device) give the number of valid points of
     each cloud; rows are padded to the tensor's point dimension and outputs past the valid length are 0.
 
-    ``exact_only`` selects the difference-form kernel on every pair instead of screen + exact re-check
-    (same output bits; default from the URED_EXACT_ONLY=1 environment knob, used for A/B timing).
+    ``exact_only`` selects the difference-form kernel on every pair instead of screen + exact re-check, ``fp32_screen`` the
+    screening pass on the FP32 pipes (nn_kernel) instead of the tensor cores (nn_tc_kernel) -- same output bits every way;
+    defaults from the URED_EXACT_ONLY=1 / URED_FP32_SCREEN=1 environment knobs, used for A/B timing and by the tests.
     """
     lib = _native.load()
     if exact_only is None:
         exact_only = os.environ.get("URED_EXACT_ONLY", "0") == "1"
+    if fp32_screen is None:
+        fp32_screen = os.environ.get("URED_FP32_SCREEN", "0") == "1"
     B, n, _ = xyz1.shape
     m = xyz2.shape[1]
     if xyz2.shape[0] != B:
@@ -82,7 +85,7 @@ def nn_forward(xyz1, xyz2, exact_only=None, len1=None, len2=None):
     idx2 = torch.empty(B, m, device=dev, dtype=torch.int32)
     ws_bytes = lib.ured_chamfer_workspace_bytes(B, n, m)
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-    flags = _native.URED_FLAG_EXACT_ONLY if exact_only else 0
+    flags = (_native.URED_FLAG_EXACT_ONLY if exact_only else 0) | (_native.URED_FLAG_FP32_SCREEN if fp32_screen else 0)
     len1, len2 = _len_arg("len1", len1, B, dev), _len_arg("len2", len2, B, dev)
     with torch.cuda.device(dev):
         rc = lib.ured_chamfer_forward(_native.ptr(xyz1), _native.ptr(xyz2), B, n, m, _native.ptr(len1), _native.ptr(len2),

@@ -29,6 +29,7 @@ if ROOT not in sys.path:
 METRIC = "Chamfer+DCD fwd+bwd Gpair/s"
 UNIT = "Gpair/s"
 FLOP_PER_PAIR = 8.0  # 3 sub, 3 mul, 2 add: the reference arithmetic
+TMEM_READ_BYTES_PER_CLK = 327.7  # per SM, measured: tools/microbench/tmem_read.cu (profiles/r02_tmem_read.txt)
 
 RETRIEVAL = {
     # name: (library shapes S, queries Q, points, description)   -- sharded over ranks, strong scaling
@@ -270,7 +271,8 @@ def measure_ffma_peak(ctx):
 
 
 def nn_roofline(ctx, x_dev, gt_dev, B, n_x, n_gt, steps, warmup, exact_only, peaks, ffma_peak, workload):
-    """The dominant kernel alone: nn_kernel (both directions, one launch) on packed clouds, L2 flushed between launches."""
+    """The dominant kernel alone (nn_tc_kernel, or nn_kernel with --exact-only / URED_NN_TC=0): both directions, one launch, on
+    packed clouds, L2 flushed between launches."""
     import ctypes
     torch, ured, lib, dev = ctx.torch, ctx.ured, ctx.lib, ctx.dev
     pk_gt, pk_x = ured.PackedClouds(gt_dev), ured.PackedClouds(x_dev)
@@ -281,11 +283,11 @@ def nn_roofline(ctx, x_dev, gt_dev, B, n_x, n_gt, steps, warmup, exact_only, pea
     scratch_bytes = lib.ured_nn_scratch_bytes(B, n_gt, n_x)
     scratch = torch.empty(max(scratch_bytes, 256), dtype=torch.uint8, device=dev)
 
-    def nn_only():
+    def nn_only(fl=flags):
         rc = lib.ured_nn_packed(gt_dev.data_ptr(), pk_gt.packed.data_ptr(), n_gt,
                                 x_dev.data_ptr(), pk_x.packed.data_ptr(), n_x, B, 1, B, None, None,
                                 d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(),
-                                scratch.data_ptr(), scratch_bytes, flags, stream)
+                                scratch.data_ptr(), scratch_bytes, fl, stream)
         ured._native.check(rc, "ured_nn_packed")
 
     ms_nn, _ = ctx.timed(nn_only, steps, warmup)
@@ -298,19 +300,51 @@ def nn_roofline(ctx, x_dev, gt_dev, B, n_x, n_gt, steps, warmup, exact_only, pea
     sm_max_mhz = float(peaks.get("sm_max_mhz") or 1965.0)
     peak = sms * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # FP32 FMA lanes x 2 FLOP x max SM clock
     traffic, traffic_src = None, None
+    tensor = v.value == 100                           # URED_NN_VARIANT_TENSOR: the screening pass runs on the tensor cores
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "nn_kernel_traffic.json")))
-        traffic, traffic_src = tj.get(workload), tj.get("source")
+        sect = tj.get("nn_tc_kernel" if tensor else "nn_kernel", tj)
+        traffic, traffic_src = sect.get(workload), sect.get("source")
     except Exception:
         pass
+    shape = {"variant": v.value, "queries_per_cta": q.value, "threads": t.value, "work_items": it.value,
+             "split_items": si.value, "candidate_splits": ns.value}
+    fp32 = {"fp32_fma_peak": peak,
+            "fp32_fma_peak_source": f"{sms} SMs x 128 FP32 lanes x 2 FLOP x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz; it has no FP32 figure)",
+            "algorithmic_tflops": achieved, "frac_of_fp32_fma_peak": achieved / peak,
+            "measured_ffma_peak": ffma_peak, "frac_of_measured_ffma_peak": (achieved / ffma_peak) if ffma_peak else None,
+            "measured_ffma_peak_source": "ured_probe_ffma (pure FFMA stream) timed in this run, best of 5"}
+    if tensor:
+        # the screen is a [queries x 32] . [candidates x 32]^T bf16 product (27 exact piece products per pair, K padded to 32):
+        # 64 executed tensor FLOP per ordered pair; every score is then read out of TMEM once (4 bytes per pair), which is what binds
+        tflop = 2.0 * 32 * pairs
+        t_ach = tflop / (ms_nn * 1e-3) / 1e12
+        t_peak = float(peaks.get("bf16_tflops") or 2250.0)
+        tmem_peak = sms * TMEM_READ_BYTES_PER_CLK * sm_max_mhz * 1e6 / 1e9
+        tmem_ach = 4.0 * pairs / (ms_nn * 1e-3) / 1e9
+        keep = (d1.clone(), d2.clone(), i1.clone(), i2.clone())
+        ms_fp32, _ = ctx.timed(lambda: nn_only(flags | ured._native.URED_FLAG_FP32_SCREEN), max(3, steps // 4), 3)   # same data, FP32-pipe screen
+        same = all(torch.equal(a, b) for a, b in zip(keep, (d1, d2, i1, i2)))
+        if not same:
+            raise SystemExit("bench: the tensor-core and FP32-pipe screening kernels disagree")
+        return {"bound": "tensor", "kernel": "nn_tc_kernel (tcgen05 screening + exact re-check, both directions, one launch%s)" % (", %d candidate ranges per cloud" % ns.value if ns.value > 1 else ""),
+                "achieved": t_ach, "peak": t_peak, "unit": "TFLOP/s", "frac": t_ach / t_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS bf16 burst figure; the kernel is timed alone)" if peaks.get("bf16_tflops") else "B200_PROFILING.md fallback: 2250 TFLOP/s dense bf16 (MEASURED_PEAKS.json absent)",
+                "flop_per_launch": tflop, "kernel_ms": ms_nn, "tpair_per_s": pairs / (ms_nn * 1e-3) / 1e12, "launch_shape": shape,
+                "fp32_screen_kernel_ms": ms_fp32, "outputs_equal_fp32_screen": same,
+                "tmem_read": {"bytes_per_launch": 4.0 * pairs, "achieved_gbs": tmem_ach, "peak_gbs": tmem_peak, "frac": tmem_ach / tmem_peak,
+                              "peak_source": f"{TMEM_READ_BYTES_PER_CLK} B/clk/SM: tools/microbench/tmem_read.cu, eight warps draining a 128 x 256 fp32 accumulator "
+                                             "with tcgen05.ld.32x32b.x32 and a running minimum (profiles/r02_tmem_read.txt)"},
+                **fp32,
+                "note": "achieved = EXECUTED tensor FLOP (2 x 32 per ordered pair: 27 exact bf16 piece products, K padded to 32) / nn_tc_kernel time; "
+                        "the reference's accounting (8 FLOP per pair, SURVEY 8d) is algorithmic_tflops, which now exceeds the FP32-FMA peak because "
+                        "the pair arithmetic left the FP32 pipes; the binding resource is the TMEM read port (tmem_read)"}
     return {"bound": "fp32_fma", "kernel": "nn_kernel (both directions, one launch%s)" % (", + merge of %d candidate splits" % ns.value if ns.value > 1 else ""),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-            "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 FLOP x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz; it has no FP32 figure)",
+            "peak_source": fp32["fp32_fma_peak_source"],
             "measured_ffma_peak": ffma_peak, "frac_of_measured_ffma_peak": (achieved / ffma_peak) if ffma_peak else None,
             "measured_ffma_peak_source": "ured_probe_ffma (pure FFMA stream) timed in this run, best of 5",
-            "flop_per_launch": flop, "kernel_ms": ms_nn, "tpair_per_s": pairs / (ms_nn * 1e-3) / 1e12,
-            "launch_shape": {"variant": v.value, "queries_per_cta": q.value, "threads": t.value, "work_items": it.value,
-                             "split_items": si.value, "candidate_splits": ns.value},
+            "flop_per_launch": flop, "kernel_ms": ms_nn, "tpair_per_s": pairs / (ms_nn * 1e-3) / 1e12, "launch_shape": shape,
             "note": "FLOP-accounted at the reference's 8 FLOP per ordered pair; the screening variant executes 6 FLOP per pair in its main loop "
                     "(executed-FLOP fraction = 0.75 x frac)"}
 

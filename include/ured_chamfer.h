@@ -68,6 +68,8 @@ extern "C" {
 #define URED_FLAG_EXACT_ONLY 1u /* skip the 3-FFMA screening pass; run the difference-form kernel on every pair */
 #define URED_FLAG_ONE_DIRECTION 4u /* ured_nn_packed: only cloud-1 points search cloud 2 (dist2/idx2 untouched, may be NULL) */
 #define URED_FLAG_NON_REG    2u /* ured_dcd_forward with lengths: clamp the DCD fractions at 1 (calc_dcd non_reg=True) */
+#define URED_FLAG_FP32_SCREEN 8u /* ured_nn_packed / ured_chamfer_forward: screen on the FP32 pipes (nn_kernel) instead of the tensor cores */
+#define URED_NN_VARIANT_TENSOR 100 /* ured_nn_launch_shape: the tensor-core screening kernel (nn_tc_kernel) */
 
 /* Ragged batches.  Entry points that take `len1` / `len2` (device int32 arrays, one entry per cloud-1 / cloud-2
  * entry, or NULL) treat cloud c as having only its first len[c] points (clamped to [0, n]); n is then the row

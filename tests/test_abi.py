@@ -101,10 +101,17 @@ def test_launch_shape_heuristic_invariants(ured):
     mid-size launches, nothing split once the grid is many waves long, scratch consistent with the plan."""
     import ctypes
     lib = ured._native.load()
+    FP32 = ured._native.URED_FLAG_FP32_SCREEN
     for B in [1, 2, 7, 16, 32, 100, 125, 640, 5000]:
         for n1, n2 in [(1, 1), (100, 200), (511, 4096), (1024, 1024), (2048, 2048), (2000, 1000), (16384, 16384), (4096, 100000)]:
             v, q, t, ns, items, split = (ctypes.c_int() for _ in range(6))
+            # the tensor-core plan (default): whole groups of 128-query tiles per item, candidate ranges of 2048, no scratch use
             assert lib.ured_nn_launch_shape(B, n1, n2, 0, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns),
+                                            ctypes.byref(items), ctypes.byref(split)) == 0
+            assert v.value == 100 and q.value % 128 == 0 and 128 <= q.value <= 2048 and split.value == 0
+            assert ns.value == -(-max(n1, n2) // 2048) and items.value == B * (-(-n1 // q.value) + -(-n2 // q.value))
+            # the FP32-pipe plan
+            assert lib.ured_nn_launch_shape(B, n1, n2, FP32, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns),
                                             ctypes.byref(items), ctypes.byref(split)) == 0
             nsplit = ns.value
             sb = lib.ured_nn_scratch_bytes(B, n1, n2)
@@ -124,6 +131,6 @@ def test_launch_shape_heuristic_invariants(ured):
     # the tail rule (split only the last partial wave) is an experiment knob, off by default: the cfg3 shard of 125 shapes
     # (1000 work items on 740 CTA slots) launches unsplit
     v, q, t, ns, items, split = (ctypes.c_int() for _ in range(6))
-    lib.ured_nn_launch_shape(125, 2048, 2048, 0, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns), ctypes.byref(items), ctypes.byref(split))
+    lib.ured_nn_launch_shape(125, 2048, 2048, FP32, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns), ctypes.byref(items), ctypes.byref(split))
     assert (items.value, split.value, ns.value) == (1000, 0, 1)
     assert lib.ured_nn_scratch_bytes(0, 8, 8) == 0 and lib.ured_nn_scratch_bytes(4, 0, 8) == 0

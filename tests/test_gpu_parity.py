@@ -20,8 +20,12 @@ def dev(t):
     return t.cuda()
 
 
+KERNELS = [False, "fp32", True]          # screening on the tensor cores (default) / on the FP32 pipes / difference form on every pair
+KERNEL_IDS = ["tensor", "fp32", "exact"]
+
+
 def run_fwd(ured, a, b, exact_only):
-    out = ured.nn_forward(dev(a).contiguous(), dev(b).contiguous(), exact_only=exact_only)
+    out = ured.nn_forward(dev(a).contiguous(), dev(b).contiguous(), exact_only=exact_only is True, fp32_screen=exact_only == "fp32")
     torch.cuda.synchronize()
     return [o.cpu().numpy() for o in out]
 
@@ -45,7 +49,7 @@ SHAPES = [  # (B, N, M, kind)
 ]
 
 
-@pytest.mark.parametrize("exact_only", [False, True], ids=["screen", "exact"])
+@pytest.mark.parametrize("exact_only", KERNELS, ids=KERNEL_IDS)
 @pytest.mark.parametrize("B,N,M,kind", SHAPES)
 def test_forward_bit_exact_vs_oracle(ured, oracle, B, N, M, kind, exact_only):
     a, b = make_clouds(0, B, N, kind), make_clouds(1, B, M, kind)
@@ -53,7 +57,7 @@ def test_forward_bit_exact_vs_oracle(ured, oracle, B, N, M, kind, exact_only):
     assert_bit_exact(run_fwd(ured, a, b, exact_only), want, f"{B}x{N}x{M}")
 
 
-@pytest.mark.parametrize("exact_only", [False, True], ids=["screen", "exact"])
+@pytest.mark.parametrize("exact_only", KERNELS, ids=KERNEL_IDS)
 def test_forward_adversarial_ties_and_duplicates(ured, oracle, exact_only):
     g = torch.Generator().manual_seed(7)
     lattice_a = torch.randint(0, 4, (2, 700, 3), generator=g).float()          # masses of exact ties
@@ -78,10 +82,13 @@ def test_forward_adversarial_ties_and_duplicates(ured, oracle, exact_only):
 
 
 def test_screen_and_exact_kernels_agree_at_full_size(ured):
-    """cfg1-sized (B=32, 2048^2) and a dense 16384^2 pair: the two kernels must give identical bits."""
-    for (B, N, M, kind) in [(32, 2048, 2048, "S"), (1, 16384, 16384, "S"), (1, 16384, 16384, "U")]:
+    """cfg1-sized (B=32, 2048^2), a dense 16384^2 pair (eight candidate ranges per cloud in the tensor-core kernel) and unequal
+    clouds: the three kernels must give identical bits."""
+    for (B, N, M, kind) in [(32, 2048, 2048, "S"), (1, 16384, 16384, "S"), (1, 16384, 16384, "U"), (3, 4100, 2049, "S"), (150, 700, 300, "U")]:
         a, b = make_clouds(20, B, N, kind), make_clouds(21, B, M, kind)
-        assert_bit_exact(run_fwd(ured, a, b, False), run_fwd(ured, a, b, True), f"full {B}x{N}x{M}")
+        want = run_fwd(ured, a, b, True)
+        assert_bit_exact(run_fwd(ured, a, b, False), want, f"tensor {B}x{N}x{M}")
+        assert_bit_exact(run_fwd(ured, a, b, "fp32"), want, f"fp32 {B}x{N}x{M}")
 
 
 def test_golden_reference_python(ured):
@@ -97,7 +104,7 @@ def test_golden_reference_cuda_op(ured):
     """Against the committed outputs of the unmodified reference CUDA op on a B200 (make_golden_gpu.py): bits for dist/idx."""
     g = np.load(os.path.join(GOLD, "chamfer_ref_cuda_b200.npz"))
     for case in ["unit_test", "timing", "ragged_tail", "lattice", "chair"]:
-        for exact_only in (False, True):
+        for exact_only in KERNELS:
             got = run_fwd(ured, torch.from_numpy(g[f"{case}_xyz1"]), torch.from_numpy(g[f"{case}_xyz2"]), exact_only)
             assert_bit_exact(got, [g[f"{case}_dist1"], g[f"{case}_dist2"], g[f"{case}_idx1"], g[f"{case}_idx2"]], case)
         xa = dev(torch.from_numpy(g[f"{case}_xyz1"])).requires_grad_()
@@ -677,6 +684,7 @@ def test_tail_split_launch_plan_returns_the_same_bits(ured, monkeypatch):
     B, n = 125, 2048
     a, b = dev(make_clouds(210, B, n, "S")), dev(make_clouds(211, B, n, "S") * 0.97)
     want = ured.nn_forward(a, b)
+    monkeypatch.setenv("URED_NN_TC", "0")            # the tail rule belongs to the FP32-pipe kernel
     monkeypatch.setenv("URED_NN_TAIL_SPLIT", "1")
     v, q, t, ns, items, split = (ctypes.c_int() for _ in range(6))
     lib.ured_nn_launch_shape(B, n, n, 0, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns), ctypes.byref(items), ctypes.byref(split))

@@ -41,10 +41,10 @@ CASES = [(4, 100, 200, "U"), (32, 2000, 1000, "U"), (32, 2048, 2048, "S"), (7, 1
 def test_kernels_bit_exact_vs_reference_op(ured, ref_op, B, N, M, kind):
     a, b = make_clouds(0, B, N, kind).cuda(), make_clouds(1, B, M, kind).cuda()
     want = ref_forward(ref_op, a, b)
-    for exact_only in (False, True):
-        got = ured.nn_forward(a, b, exact_only=exact_only)
+    for kernel in ("tensor", "fp32", "exact"):     # screening on the tensor cores / on the FP32 pipes / difference form on every pair
+        got = ured.nn_forward(a, b, exact_only=kernel == "exact", fp32_screen=kernel == "fp32")
         for g, w, name in zip(got, want, ["dist1", "dist2", "idx1", "idx2"]):
-            assert torch.equal(g, w), f"{name} differs from the reference op (exact_only={exact_only}): {(g != w).sum().item()} entries"
+            assert torch.equal(g, w), f"{name} differs from the reference op ({kernel} kernel): {(g != w).sum().item()} entries"
 
 
 def test_c_oracle_bit_exact_vs_reference_op(oracle, ref_op):

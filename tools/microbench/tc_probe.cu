@@ -144,51 +144,57 @@ int main() {
         printf("test0 plain bf16 [128x32]x[256x32]^T: max |err| = %.3e, entries off by > 1e-4: %d of %d, out[0][0..3] = %g %g %g %g\n", maxerr, bad,
                M * N, out[0], out[1], out[2], out[3]);
     }
-    // ---- tests 1, 2: the split scheme
-    for (int test = 1; test <= 2; test++) {
-        const double shift = test == 1 ? 0.0 : 1000.0;
-        std::vector<float> q(M * 3), c(N * 3), W(N);
-        for (auto &v : q) v = (float)(urand() * 2 - 1 + shift);
-        for (auto &v : c) v = (float)(urand() * 2 - 1 + shift);
-        double S = 0, maxc = 0;
-        for (int j = 0; j < N; j++) {
-            W[j] = fmaf(c[j * 3 + 2], c[j * 3 + 2], fmaf(c[j * 3 + 1], c[j * 3 + 1], c[j * 3] * c[j * 3]));
-            maxc = fmax(maxc, sqrt((double)W[j]));
-        }
-        std::vector<uint16_t> A(M * K, 0), B(N * K, 0);
-        // per coordinate 8 products a_i b_j with i + j <= 5 (pieces numbered from 1): (1,1) (1,2) (2,1) (1,3) (2,2) (3,1) (2,3) (3,2)
-        const int pa[8] = {0, 0, 1, 0, 1, 2, 1, 2}, pb[8] = {0, 1, 0, 2, 1, 0, 2, 1};
-        for (int i = 0; i < M; i++) {
-            for (int d = 0; d < 3; d++) {
-                uint16_t p[3]; split3(-2.0f * q[i * 3 + d], p);
-                for (int t = 0; t < 8; t++) A[i * K + d * 8 + t] = p[pa[t]];
-            }
-            for (int t = 0; t < 3; t++) A[i * K + 24 + t] = bf16_rn(1.0f);
-        }
-        for (int j = 0; j < N; j++) {
-            for (int d = 0; d < 3; d++) {
-                uint16_t p[3]; split3(c[j * 3 + d], p);
-                for (int t = 0; t < 8; t++) B[j * K + d * 8 + t] = p[pb[t]];
-            }
-            uint16_t p[3]; split3(W[j], p);
-            for (int t = 0; t < 3; t++) B[j * K + 24 + t] = p[t];
-        }
-        std::vector<float> out;
-        const int st = run(A, B, out);
-        if (st) { printf("test%d: status %d\n", test, st); return 1; }
-        double maxerr = 0, maxrel = 0;
-        for (int i = 0; i < M; i++) {
-            const double qn = sqrt((double)q[i * 3] * q[i * 3] + (double)q[i * 3 + 1] * q[i * 3 + 1] + (double)q[i * 3 + 2] * q[i * 3 + 2]);
-            S = qn + maxc;
+    // ---- the split scheme on several input distributions; prints the worst error in units of S^2 (S = |q| + max |c|)
+    struct Dist { const char *name; double shift, sq, sc; };
+    const Dist dists[] = {{"unit cube", 0, 1, 1}, {"shift +1000", 1000, 1, 1}, {"shift -37.5", -37.5, 1, 1}, {"queries x 1e3", 0, 1e3, 1},
+                          {"candidates x 1e3", 0, 1, 1e3}, {"both x 1e-3", 0, 1e-3, 1e-3}, {"both x 1e6", 0, 1e6, 1e6}, {"shift 3, x 1e-2", 3, 1e-2, 1e-2}};
+    double worst = 0;
+    for (const Dist &ds : dists) {
+        double maxrel = 0, maxerr = 0;
+        for (int seed = 0; seed < 4; seed++) {
+            std::vector<float> q(M * 3), c(N * 3), W(N);
+            for (auto &v : q) v = (float)((urand() * 2 - 1) * ds.sq + ds.shift);
+            for (auto &v : c) v = (float)((urand() * 2 - 1) * ds.sc + ds.shift);
+            double maxc = 0;
             for (int j = 0; j < N; j++) {
-                const double ref = (double)W[j] - 2.0 * ((double)q[i * 3] * c[j * 3] + (double)q[i * 3 + 1] * c[j * 3 + 1] + (double)q[i * 3 + 2] * c[j * 3 + 2]);
-                const double err = fabs(out[(size_t)i * N + j] - ref);
-                maxerr = fmax(maxerr, err);
-                maxrel = fmax(maxrel, err / (S * S));
+                W[j] = fmaf(c[j * 3 + 2], c[j * 3 + 2], fmaf(c[j * 3 + 1], c[j * 3 + 1], c[j * 3] * c[j * 3]));
+                maxc = fmax(maxc, sqrt((double)W[j]));
+            }
+            std::vector<uint16_t> A(M * K, 0), B(N * K, 0);
+            // per coordinate 8 products a_i b_j with i + j <= 5 (pieces numbered from 1): (1,1) (1,2) (2,1) (1,3) (2,2) (3,1) (2,3) (3,2)
+            const int pa[8] = {0, 0, 1, 0, 1, 2, 1, 2}, pb[8] = {0, 1, 0, 2, 1, 0, 2, 1};
+            for (int i = 0; i < M; i++) {
+                for (int d = 0; d < 3; d++) {
+                    uint16_t p[3]; split3(-2.0f * q[i * 3 + d], p);
+                    for (int t = 0; t < 8; t++) A[i * K + d * 8 + t] = p[pa[t]];
+                }
+                for (int t = 0; t < 3; t++) A[i * K + 24 + t] = bf16_rn(1.0f);
+            }
+            for (int j = 0; j < N; j++) {
+                for (int d = 0; d < 3; d++) {
+                    uint16_t p[3]; split3(c[j * 3 + d], p);
+                    for (int t = 0; t < 8; t++) B[j * K + d * 8 + t] = p[pb[t]];
+                }
+                uint16_t p[3]; split3(W[j], p);
+                for (int t = 0; t < 3; t++) B[j * K + 24 + t] = p[t];
+            }
+            std::vector<float> out;
+            const int st = run(A, B, out);
+            if (st) { printf("split scheme: status %d\n", st); return 1; }
+            for (int i = 0; i < M; i++) {
+                const double qn = sqrt((double)q[i * 3] * q[i * 3] + (double)q[i * 3 + 1] * q[i * 3 + 1] + (double)q[i * 3 + 2] * q[i * 3 + 2]);
+                const double S = qn + maxc;
+                for (int j = 0; j < N; j++) {
+                    const double ref = (double)W[j] - 2.0 * ((double)q[i * 3] * c[j * 3] + (double)q[i * 3 + 1] * c[j * 3 + 1] + (double)q[i * 3 + 2] * c[j * 3 + 2]);
+                    const double err = fabs(out[(size_t)i * N + j] - ref);
+                    maxerr = fmax(maxerr, err);
+                    maxrel = fmax(maxrel, err / (S * S));
+                }
             }
         }
-        printf("test%d split scheme (shift %g): max |s_tc - s_f64| = %.3e, max err / S^2 = %.3e = 2^%.2f  (fp32 FMA chain bound: 6u = 2^-21.4)\n", test,
-               shift, maxerr, maxrel, log2(maxrel));
+        printf("split scheme, %-18s: max |s_tc - s_f64| = %.3e, max err / S^2 = 2^%.2f\n", ds.name, maxerr, log2(maxrel));
+        worst = fmax(worst, maxrel);
     }
+    printf("WORST err / S^2 = 2^%.2f  (allowed by the screening bound: 6 u = 2^-21.42; eps = 32 u S^2)\n", log2(worst));
     return 0;
 }
