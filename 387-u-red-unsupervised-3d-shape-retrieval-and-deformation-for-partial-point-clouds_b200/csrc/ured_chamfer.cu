@@ -600,10 +600,16 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// a wait that cannot hang the GPU: a protocol bug traps (the launch fails) instead of spinning forever
+// a wait that cannot hang the GPU: a protocol bug traps (the launch fails) after ten seconds instead of spinning forever
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 template <bool RELAXED = false>
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
     uint32_t done = 0;
+    unsigned long long t0 = 0;
     for (unsigned spins = 0; !done; spins++) {
         if (RELAXED && spins > 0) __nanosleep(200);   // off the critical path: leave the issue slots to the TMEM readers
         asm volatile(
@@ -613,7 +619,11 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
-        if (!done && spins > (1u << 24)) __trap();   // try_wait itself blocks for a while; 2^24 polls is many seconds
+        if (!done && (spins & 0xfffu) == 0xfffu) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 10000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {

@@ -65,7 +65,7 @@ extern "C" {
 #define URED_E_RANGE     (-4) /* k, n_lambda, ... out of the supported range */
 
 /* flags for the forward entry points */
-#define URED_FLAG_EXACT_ONLY 1u /* skip the 3-FFMA screening pass; run the difference-form kernel on every pair */
+#define URED_FLAG_EXACT_ONLY 1u /* skip the screening pass; run the difference-form kernel on every pair (FP32 pipes) */
 #define URED_FLAG_ONE_DIRECTION 4u /* ured_nn_packed: only cloud-1 points search cloud 2 (dist2/idx2 untouched, may be NULL) */
 #define URED_FLAG_NON_REG    2u /* ured_dcd_forward with lengths: clamp the DCD fractions at 1 (calc_dcd non_reg=True) */
 #define URED_FLAG_FP32_SCREEN 8u /* ured_nn_packed / ured_chamfer_forward: screen on the FP32 pipes (nn_kernel) instead of the tensor cores */
@@ -84,8 +84,9 @@ const char *ured_last_error_string(void);
 unsigned long long ured_kernel_launches(void);
 
 /* ---- packed clouds ---------------------------------------------------------------------
- * The nearest-neighbour kernel stages the opposing cloud through shared memory with TMA bulk
- * copies from a packed, padded structure-of-arrays image: per cloud one block
+ * The nearest-neighbour kernels read both clouds from a packed, padded structure-of-arrays image (the tensor-core
+ * kernel builds its bf16 operand rows from it and copies X|Y|Z into shared memory with TMA bulk copies; the
+ * FP32-pipe kernel streams all four arrays through shared memory the same way): per cloud one block
  *     X[np] | Y[np] | Z[np] | W[np] | tail[32]      (floats; np = n rounded up to 32)
  * with W = x^2+y^2+z^2, padding = copies of the last point, tail[0] = max W of the cloud.
  * Blocks are independent: a pointer to block i is a valid packed image of clouds i, i+1, ...
@@ -99,20 +100,29 @@ int ured_pack_clouds(const float *xyz, int count, int n, const int *len, void *p
  *                      point in cloud 2 (lowest index on ties);  dist2/idx2: [B, n2] vice versa.
  * Queries are read from the packed images too, so xyz1 / xyz2 may be NULL when the corresponding image is given
  * (xyz1 is needed only with URED_FLAG_ONE_DIRECTION and packed1 == NULL).
- * Results are bit-identical to NmDistanceKernel (chamfer3D.cu:12-134) for finite inputs.  Non-finite coordinates:
+ * Results are bit-identical to NmDistanceKernel (chamfer3D.cu:12-134) for finite inputs, whichever kernel runs:
+ *   default                  nn_tc_kernel: the screening scores |c|^2 - 2 q.c come from the tensor cores (tcgen05.mma on
+ *                            exact bf16x3 operand splits, fp32 accumulators in TMEM), the winning 32-candidate chunk of every
+ *                            query is then evaluated in the reference's exact difference form; needs no scratch;
+ *   URED_FLAG_FP32_SCREEN    nn_kernel: the same screen with packed FP32 FMAs;
+ *   URED_FLAG_EXACT_ONLY     nn_kernel: the difference form on every pair.
+ * Non-finite coordinates:
  * memory-safe (indices stay in range) but unspecified -- the reference admits a NaN distance only as the first
  * candidate of each of its 512-candidate tiles (chamfer3D.cu:36,126), an artefact this library does not reproduce;
  * the Python layer offers an opt-in check that raises instead (URED_CHECK_FINITE=1).
  *
- * For shapes whose grid would be too small (few pairs), very large clouds, and launches whose last wave of CTAs would
- * be mostly empty, the candidate range of some or all work items is split over several CTAs and merged afterwards;
- * that needs `scratch`: ured_nn_scratch_bytes(B, n1, n2) bytes (0 for most shapes, in which case scratch may be
- * NULL), 256-byte aligned. */
+ * FP32-pipe kernels only: for shapes whose grid would be too small (few pairs), very large clouds, and launches whose
+ * last wave of CTAs would be mostly empty, the candidate range of some or all work items is split over several CTAs and
+ * merged afterwards; that needs `scratch`: ured_nn_scratch_bytes(B, n1, n2) bytes (0 for most shapes, in which case
+ * scratch may be NULL), 256-byte aligned.  (The tensor-core kernel scans clouds of more than 2048 candidates range by
+ * range inside one CTA and ignores scratch.) */
 size_t ured_nn_scratch_bytes(int B, int n1, int n2);
-/* The launch plan ured_nn_packed will use for this problem (reporting / tests): kernel variant id, queries per CTA,
- * threads per CTA, the number of work items (pair, direction, query tile), how many of them -- always the LAST ones of
- * the launch -- are cut into `nsplit` candidate ranges, and nsplit itself (1 when nothing is split).  Any output
- * pointer may be NULL. */
+/* The launch plan ured_nn_packed will use for this problem and these flags (reporting / tests).  FP32-pipe kernels:
+ * kernel variant id, queries per CTA, threads per CTA, the number of work items (pair, direction, query tile), how many
+ * of them -- always the LAST ones of the launch -- are cut into `nsplit` candidate ranges, and nsplit itself (1 when
+ * nothing is split).  Tensor-core kernel: variant = URED_NN_VARIANT_TENSOR, queries per work item (a group of 128-query
+ * tiles), threads per CTA, work items (pair, direction, query group; taken in turn by one persistent CTA per SM),
+ * nsplit = candidate ranges of 2048 scanned one after the other, split_items = 0.  Any output pointer may be NULL. */
 int ured_nn_launch_shape(int B, int n1, int n2, unsigned flags, int *variant, int *queries_per_cta, int *threads, int *nsplit,
                          int *items, int *split_items);
 int ured_nn_packed(const float *xyz1, const void *packed1, int n1,

@@ -36,7 +36,7 @@ def test_gpu_arm_line():
     d = run_bench("--steps", "3", "--warmup", "3", "--no-cpu-baseline")
     assert BASE_KEYS | {"roofline", "clocks"} <= set(d) and "impl" not in d
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["scaling"] == "weak" and d["dtype"] == "f32" and d["value"] > 0
-    assert d["gpu_launches"] == 4 * 3                       # pack, nn_kernel, dcd_fwd_kernel, grad_smem_kernel per step
+    assert d["gpu_launches"] == 4 * 3                       # pack, nn_tc_kernel, dcd_fwd_kernel, grad_gather_kernel per step
     r = d["roofline"]
     assert r["unit"] == "TFLOP/s" and 0.3 < r["frac"] < 1.2 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     e = d["e2e"]
