@@ -687,14 +687,20 @@ __device__ __forceinline__ float min32(const uint32_t (&v)[32]) {
                  : "memory")
 
 #ifdef URED_TC_PROFILE
+__device__ long long g_tc_trace[4][24];
 __device__ long long g_tc_prof[16];   // [0] items [1] build [2] wait full [3] tmem read + reduce [4] merge + re-check [5] total  (thread 0 of CTA 0)
 #define TC_T(x) const long long x = clock64()
 #define TC_ADD(i, a, b) do { if (tid == 0) pacc[i] += (b) - (a); } while (0)            // (registers: a global update here would stall the thread)
 #define TC_ADDM(i, a, b) do { if (is_mma_thread && mma_id == 0) pacc[i] += (b) - (a); } while (0)
-#define TC_PROF_DECL long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define TC_PROF_DECL long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; int trace_n = 0
+// timeline of the SECOND work item of CTA 0: role r (0/1 reader sets, 2 MMA warp 0, 3 resolvers) stamps the end of every query tile
+#define TC_TRACE_RESET trace_n = 0
+#define TC_TRACE(role) do { if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0 && item == (int)(blockIdx.x + gridDim.x) && trace_n < 24) g_tc_trace[role][trace_n++] = clock64(); } while (0)
 #define TC_PROF_FLUSH do { if (blockIdx.x == 0 && (tid == 0 || (is_mma_thread && mma_id == 0))) for (int i_ = 0; i_ < 10; i_++) atomicAdd((unsigned long long *)&g_tc_prof[i_], (unsigned long long)pacc[i_]); } while (0)
 #else
 #define TC_PROF_DECL
+#define TC_TRACE_RESET
+#define TC_TRACE(role)
 #define TC_PROF_FLUSH
 #define TC_ADDM(i, a, b)
 #define TC_T(x)
@@ -830,12 +836,17 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + (SPLIT ? 1 : NSETS) + 4), 1)
         TC_T(t_built);
         TC_ADD(1, t_item, t_built);
         TC_ADD(0, 0, 1);
+        TC_TRACE_RESET;
+        if (is_query_thread) { TC_TRACE(set); } else if (is_mma_warp) { if (mma_id == 0) TC_TRACE(2); } else { TC_TRACE(3); }
 
         if (is_mma_warp) {   // the whole warp walks the loop (it stays converged for the block barriers); lane 0 issues
             uint32_t tc = tile_ctr, qc = qt_ctr;
             for (int qt = qt_lo; qt < qt_search; qt++, qc++) {
+                TC_T(t_a0);
                 mbar_wait_bounded(&a_bar[qc & 1], (qc >> 1) & 1);
                 tc_fence_after();
+                TC_T(t_a1);
+                TC_ADDM(9, t_a0, t_a1);
                 const uint32_t a_addr = smem_u32(Abuf + (qc & 1) * (kTcSmemA / 2));
                 for (int j = 0; j < ntiles; j++, tc++) {
                     if (kMmaWarps > 1 && (int)(tc % kMmaWarps) != mma_id) continue;
@@ -863,6 +874,7 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + (SPLIT ? 1 : NSETS) + 4), 1)
                     TC_T(t_m3);
                     TC_ADDM(8, t_m2, t_m3);
                 }
+                if (mma_id == 0) TC_TRACE(2);
             }
         }
         if (is_query_thread) {
@@ -912,6 +924,7 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + (SPLIT ? 1 : NSETS) + 4), 1)
                 mbar_arrive(&r_bar[slot]);
                 TC_T(t_r1);
                 TC_ADD(4, t_r0, t_r1);
+                TC_TRACE(set);
             }
             TC_T(t_end);
             TC_ADD(5, t_item, t_end);
@@ -1011,6 +1024,7 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + (SPLIT ? 1 : NSETS) + 4), 1)
                     out_d[j] = bd;
                     out_i[j] = bi;
                 }
+                TC_TRACE(3);
             }
             // tiles without a valid query (or an empty candidate cloud): the reference leaves its zero-filled outputs untouched
             if (last_range)
@@ -2355,6 +2369,10 @@ int ured_debug_tc_profile(long long *out16) {
     long long zero[16] = {0};
     cudaMemcpyFromSymbol(out16, g_tc_prof, sizeof(zero));
     cudaMemcpyToSymbol(g_tc_prof, zero, sizeof(zero));
+    return 0;
+}
+int ured_debug_tc_trace(long long *out96) {
+    cudaMemcpyFromSymbol(out96, g_tc_trace, sizeof(long long) * 96);
     return 0;
 }
 #endif
