@@ -606,12 +606,12 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-template <bool RELAXED = false>
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
     uint32_t done = 0;
     unsigned long long t0 = 0;
     for (unsigned spins = 0; !done; spins++) {
-        if (RELAXED && spins > 0) __nanosleep(200);   // off the critical path: leave the issue slots to the TMEM readers
+        if (SLEEP_NS > 0 && spins > 0) __nanosleep(SLEEP_NS);   // leave the issue slots to the TMEM readers
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -942,7 +942,7 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + (SPLIT ? 1 : NSETS) + 4), 1)
                 const bool feed = qt + 2 < qt_search;
                 if (feed) load_query(qt + 2, fx, fy, fz);
                 const int slot = qc & 1;
-                mbar_wait_bounded<true>(&r_bar[slot], (qc >> 1) & 1);
+                mbar_wait_bounded<200>(&r_bar[slot], (qc >> 1) & 1);
                 float best = x_best[slot][0][t], second = x_second[slot][0][t];
                 int bchunk = x_chunk[slot][0][t];
 #pragma unroll
