@@ -10,7 +10,12 @@
 //
 // Kernel plan (DESIGN.md has the numbers):
 //   pack_kernel   xyz[count,n,3] -> padded SoA image X|Y|Z|W (+ max W per cloud)     HBM-bound, tiny
-//   nn_kernel     both directions of the nearest-neighbour search in ONE launch.  Each CTA owns
+//   nn_tc_kernel  (default) both directions of the nearest-neighbour search in ONE launch, the screening scores
+//                 |c|^2 - 2 q.c computed by the TENSOR CORES: exact bf16x3 operand splits (27 products per pair,
+//                 K = 32), tcgen05.mma kind::f16 into fp32 accumulators in TMEM; persistent warp-specialised CTAs
+//                 (TMEM readers keeping 32-candidate chunk minima, MMA issuers, resolver warps doing the exact
+//                 difference-form re-check of the winning chunk).  Output bits identical to the kernels below.
+//   nn_kernel     the same search on the FP32 pipes (URED_FLAG_FP32_SCREEN / URED_FLAG_EXACT_ONLY).  Each CTA owns
 //                 T*R query points of one (pair, direction), streams the opposing cloud through
 //                 shared memory with TMA bulk copies (cp.async.bulk + mbarrier, 2 stages) and
 //                 evaluates packed FP32 math (FADD2/FMUL2/FFMA2) with a register-resident chunk
