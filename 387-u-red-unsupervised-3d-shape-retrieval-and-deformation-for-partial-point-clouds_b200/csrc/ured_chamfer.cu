@@ -1624,6 +1624,12 @@ __global__ void __launch_bounds__(kGradSmemThreads, 3) grad_gather_kernel(const 
     if (v1 == 0 || v2 == 0) { v1 = 0; v2 = 0; }          // an empty side: no matches, zero gradients
     const int q2 = p.one_dir ? 0 : v2;                   // cloud-2 points that searched cloud 1
 
+#ifdef URED_TC_PROFILE
+    const long long gp0 = clock64();
+#define GRAD_STAMP(i, since) do { __syncthreads(); if (blockIdx.x == 7 && tid == 0) g_tc_prof[i] = clock64() - (since); } while (0)
+#else
+#define GRAD_STAMP(i, since)
+#endif
     // ---- 1. histogram of the argmins (bins = the points being chosen) ----------------------------------------------
     for (int k = tid; k < nt; k += kGradSmemThreads) seg[k] = 0;
     __syncthreads();
@@ -1633,8 +1639,10 @@ __global__ void __launch_bounds__(kGradSmemThreads, 3) grad_gather_kernel(const 
     for (int i = tid; i < q2; i += kGradSmemThreads) atomicAdd(&seg[n2 + idx2[i]], 1);
     __syncthreads();
     // ---- 2. segment starts ------------------------------------------------------------------------------------------
+    GRAD_STAMP(10, gp0);
     block_exclusive_scan<kGradSmemThreads>(seg, n2, scan_scratch);
     block_exclusive_scan<kGradSmemThreads>(seg + n2, n1, scan_scratch);
+    GRAD_STAMP(11, gp0);
     // ---- 3. own terms + grouping ------------------------------------------------------------------------------------
     GradSide s1, s2;
     s1.xyz_own = xyz1; s1.xyz_oth = xyz2; s1.idx = idx1; s1.v_own = v1;
@@ -1655,10 +1663,12 @@ __global__ void __launch_bounds__(kGradSmemThreads, 3) grad_gather_kernel(const 
     grad_own_terms(s1, vec, n1, seg, lst, true);
     grad_own_terms(s2, vec + n1 * 3, n2, seg + n2, lst + n1, true);
     __syncthreads();
+    GRAD_STAMP(12, gp0);
     // ---- 4. gather ----------------------------------------------------------------------------------------------------
     // cloud-1 point j was chosen by the cloud-2 points filed in bins seg[n2 + j]; cloud-2 point j by the cloud-1 points in seg[j]
     grad_gather_side(vec, vec + n1 * 3, n1, seg + n2, lst + n1, idx2, q2, p.grad[0] + b * n1 * 3);
     grad_gather_side(vec + n1 * 3, vec, n2, seg, lst, idx1, v1, p.grad[1] + b * n2 * 3);
+    GRAD_STAMP(13, gp0);
 }
 
 // ---- one CTA per (pair, cloud) --------------------------------------------------------------------------------------
