@@ -821,11 +821,22 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + (SPLIT ? 1 : NSETS) + 4), 1)
                 tma_bulk_g2s(Cz, csoa + 2 * (size_t)ncp_max + k_lo, bytes, &c_bar);
             }
             // operand image of the candidates; rows past the padded cloud can never win (W = 3e38, coordinates 0)
-#pragma unroll 2
-            for (int r = tid; r < ntiles * kTcN; r += kTcThreads) {
-                unsigned char *row = tc_row(Bimg, r);
-                if (r < ncp) tc_write_candidate(row, csoa[k_lo + r], csoa[ncp_max + k_lo + r], csoa[2 * (size_t)ncp_max + k_lo + r], csoa[3 * (size_t)ncp_max + k_lo + r]);
-                else tc_write_candidate(row, 0.0f, 0.0f, 0.0f, 3.0e38f);
+            // (all of a thread's rows are fetched before the first is converted: the build is one memory round trip, not five)
+            constexpr int kRowsPerThread = (kTcMaxC + kTcThreads - 1) / kTcThreads;
+            float bx[kRowsPerThread], by[kRowsPerThread], bz[kRowsPerThread], bw[kRowsPerThread];
+#pragma unroll
+            for (int i = 0; i < kRowsPerThread; i++) {
+                const int r = tid + i * kTcThreads;
+                const bool real = r < ncp;
+                bx[i] = real ? csoa[k_lo + r] : 0.0f;
+                by[i] = real ? csoa[ncp_max + k_lo + r] : 0.0f;
+                bz[i] = real ? csoa[2 * (size_t)ncp_max + k_lo + r] : 0.0f;
+                bw[i] = real ? csoa[3 * (size_t)ncp_max + k_lo + r] : 3.0e38f;
+            }
+#pragma unroll
+            for (int i = 0; i < kRowsPerThread; i++) {
+                const int r = tid + i * kTcThreads;
+                if (r < ntiles * kTcN) tc_write_candidate(tc_row(Bimg, r), bx[i], by[i], bz[i], bw[i]);
             }
             if (is_resolver) {   // operand rows of the first two query tiles (the later ones follow during the pass)
 #pragma unroll
