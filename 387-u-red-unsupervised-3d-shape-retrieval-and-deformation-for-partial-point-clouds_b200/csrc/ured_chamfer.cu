@@ -702,13 +702,15 @@ __device__ long long g_tc_prof[16];   // [0] items [1] build [2] wait full [3] t
 #define TC_T(x) const long long x = clock64()
 #define TC_ADD(i, a, b) do { if (tid == 0) pacc[i] += (b) - (a); } while (0)            // (registers: a global update here would stall the thread)
 #define TC_ADDM(i, a, b) do { if (is_mma_thread && mma_id == 0) pacc[i] += (b) - (a); } while (0)
-#define TC_PROF_DECL long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; int trace_n = 0
+#define TC_PROF_DECL long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; int trace_n = 0, fine_n = 0
 // timeline of the SECOND work item of CTA 0: role r (0/1 reader sets, 2 MMA warp 0, 3 resolvers) stamps the end of every query tile
-#define TC_TRACE_RESET trace_n = 0
+#define TC_TRACE_RESET trace_n = 0; fine_n = 0
+#define TC_FINE(v) do { if (blockIdx.x == 0 && tid == 0 && item == (int)(blockIdx.x + gridDim.x) && qt == qt_lo + 3 && fine_n < 24) g_tc_trace[1][fine_n++] = (v); } while (0)
 #define TC_TRACE(role) do { if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0 && item == (int)(blockIdx.x + gridDim.x) && trace_n < 24) g_tc_trace[role][trace_n++] = clock64(); } while (0)
 #define TC_PROF_FLUSH do { if (blockIdx.x == 0 && (tid == 0 || (is_mma_thread && mma_id == 0))) for (int i_ = 0; i_ < 10; i_++) atomicAdd((unsigned long long *)&g_tc_prof[i_], (unsigned long long)pacc[i_]); } while (0)
 #else
 #define TC_PROF_DECL
+#define TC_FINE(v)
 #define TC_TRACE_RESET
 #define TC_TRACE(role)
 #define TC_PROF_FLUSH
@@ -858,7 +860,7 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + (SPLIT ? 1 : NSETS) + 4), 1)
         TC_ADD(1, t_item, t_built);
         TC_ADD(0, 0, 1);
         TC_TRACE_RESET;
-        if (is_query_thread) { TC_TRACE(set); } else if (is_mma_warp) { if (mma_id == 0) TC_TRACE(2); } else { TC_TRACE(3); }
+        if (is_query_thread) { if (set == 0) TC_TRACE(0); } else if (is_mma_warp) { if (mma_id == 0) TC_TRACE(2); } else { TC_TRACE(3); }
 
         if (is_mma_warp) {   // the whole warp walks the loop (it stays converged for the block barriers); lane 0 issues
             uint32_t tc = tile_ctr, qc = qt_ctr;
@@ -909,9 +911,13 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + (SPLIT ? 1 : NSETS) + 4), 1)
                     if (!SPLIT && (int)(tc % NSETS) != set) continue;
                     const uint32_t acc = tc % kTcAcc, use = tc / kTcAcc;
                     TC_T(t_w0);
+                    TC_FINE(t_w0);
                     mbar_wait_bounded(&full_bar[acc], use & 1);
+                    TC_T(t_wm);
+                    TC_FINE(t_wm);
                     tc_fence_after();
                     TC_T(t_w1);
+                    TC_FINE(t_w1);
                     TC_ADD(2, t_w0, t_w1);
                     const int c_lo = SPLIT ? set * kChunksPerSet : 0;
                     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + acc * kTcN + c_lo * 32;
@@ -935,6 +941,7 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + (SPLIT ? 1 : NSETS) + 4), 1)
                     tc_fence_before();
                     mbar_arrive(&empty_bar[acc]);
                     TC_T(t_w2);
+                    TC_FINE(t_w2);
                     TC_ADD(3, t_w1, t_w2);
                 }
                 TC_T(t_r0);
@@ -945,7 +952,7 @@ __global__ void __launch_bounds__(32 * (4 * NSETS + (SPLIT ? 1 : NSETS) + 4), 1)
                 mbar_arrive(&r_bar[slot]);
                 TC_T(t_r1);
                 TC_ADD(4, t_r0, t_r1);
-                TC_TRACE(set);
+                if (set == 0) TC_TRACE(0);
             }
             TC_T(t_end);
             TC_ADD(5, t_item, t_end);

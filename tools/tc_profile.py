@@ -28,6 +28,12 @@ for rep in range(3):
 lib.ured_debug_tc_trace(trace)
 t = [list(trace)[r * 24:(r + 1) * 24] for r in range(4)]
 t0 = min(r[0] for r in t if r[0])
-for name, r in zip(("reader set 0", "reader set 1", "MMA warp 0 ", "resolvers   "), t):
+for name, r in zip(("reader set 0", "(fine)      ", "MMA warp 0 ", "resolvers   "), t):
     stamps = [v - t0 for v in r if v]
+    if name.startswith("(fine)"):
+        # reader set 0, fourth query tile of the item: per own tile [loop top, barrier seen, fence done, accumulator handed back]
+        print("reader set 0, one query tile, per own tile: " + " | ".join(
+            f"wait {stamps[i+1]-stamps[i]} fence {stamps[i+2]-stamps[i+1]} read {stamps[i+3]-stamps[i+2]}" + (f" gap {stamps[i+4]-stamps[i+3]}" if i + 4 < len(stamps) else "")
+            for i in range(0, len(stamps) - 3, 4)))
+        continue
     print(name, "start", stamps[0], "query-tile ends:", " ".join(str(b - a) for a, b in zip(stamps, stamps[1:])), "| last", stamps[-1])
