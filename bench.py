@@ -374,7 +374,7 @@ def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, 
     S0, Q0, n, desc = RETRIEVAL[name]
     S, Q, k = S or S0, Q or Q0, 10
     heavy = 2.0 * Q * S * n * n > 5e11            # more than ~70 ms per step on one GPU: fewer steps
-    st_n, wu_n = (max(2, min(steps, 5)), 2) if heavy else (max(steps, 20), max(warmup, 5))
+    st_n, wu_n = (max(2, min(steps, 5)), 2) if heavy else (max(steps, 100), max(warmup, 10))
     lo, hi = ured.shard_bounds(S, ctx.world, ctx.rank)
     shard_x = library_rows(lo, hi, n, dev)
     shard = ured.PackedClouds(shard_x) if shard_x is not None else None
@@ -411,8 +411,16 @@ def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, 
         engine.submit(t, host_out=host[state["i"] % depth])
         state["i"] += 1
 
-    ms_step, launches = ctx.timed(step_device, st_n, wu_n, flush=False, whole_loop=True, finish=engine.drain)
-    ms_e2e, _ = ctx.timed(step_e2e, st_n, wu_n, flush=False, whole_loop=True, finish=engine.drain)
+    def median_of(fn_step, reps):
+        # a light query batch is ~0.1 ms: one host hiccup inside a 50-step loop moves the figure by 10 %, so such workloads are
+        # timed `reps` times (each loop: st_n steps, one event pair, max over ranks) and the median loop is reported
+        runs = [ctx.timed(fn_step, st_n, wu_n, flush=False, whole_loop=True, finish=engine.drain) for _ in range(reps)]
+        runs.sort(key=lambda r: r[0])
+        return runs[len(runs) // 2]
+
+    reps = 1 if heavy else 3
+    ms_step, launches = median_of(step_device, reps)
+    ms_e2e, _ = median_of(step_e2e, reps)
     ms_query, _ = ctx.timed(lambda: engine.query(tg_dev), st_n, wu_n, flush=False)      # one batch at a time: the latency of a query
     v, i = engine.query(tg_dev)
     engine.check()
@@ -420,7 +428,7 @@ def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, 
     ids = i.cpu().contiguous()
     sha = hashlib.sha1(ids.numpy().tobytes()).hexdigest()
     rec = {"workload": f"{name}: {desc}", "library_shapes": S, "queries": Q, "points": n, "top_k": k, "n_gpus": ctx.world,
-           "scaling": "strong", "steps": st_n, "warmup": wu_n, "ms_per_step": ms_step, "pipeline_depth": depth,
+           "scaling": "strong", "steps": st_n, "warmup": wu_n, "timed_loops": reps, "ms_per_step": ms_step, "pipeline_depth": depth,
            "ms_per_query_one_at_a_time": ms_query,
            "value": pairs_per_step / (ms_step * 1e-3) / 1e9, "unit": UNIT,
            "e2e": {"ms_per_step": ms_e2e, "value": pairs_per_step / (ms_e2e * 1e-3) / 1e9, "h2d_bytes_per_step": int(tg_pin.numel() * 4),
@@ -444,7 +452,8 @@ def retrieval_record(ctx, name, steps, warmup, exchange="peer", S=None, Q=None, 
             for e in [e1] + e1.lanes:
                 e.world, e.exchange = 1, "none"        # a single-rank engine inside a multi-rank job
             st_1, wu_1 = (2, 1) if heavy else (st_n, wu_n)
-            ms_1, _ = ctx.timed(lambda: e1.submit(tg_dev), st_1, max(wu_1, depth), flush=False, collective=False, whole_loop=True, finish=e1.drain)
+            ms_1 = sorted(ctx.timed(lambda: e1.submit(tg_dev), st_1, max(wu_1, depth), flush=False, collective=False, whole_loop=True, finish=e1.drain)[0]
+                          for _ in range(reps))[reps // 2]
             ms_1q, _ = ctx.timed(lambda: e1.query(tg_dev), st_1, wu_1, flush=False, collective=False)
             v1, i1 = e1.query(tg_dev)
             torch.cuda.synchronize()
