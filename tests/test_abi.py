@@ -134,3 +134,25 @@ def test_launch_shape_heuristic_invariants(ured):
     lib.ured_nn_launch_shape(125, 2048, 2048, FP32, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns), ctypes.byref(items), ctypes.byref(split))
     assert (items.value, split.value, ns.value) == (1000, 0, 1)
     assert lib.ured_nn_scratch_bytes(0, 8, 8) == 0 and lib.ured_nn_scratch_bytes(4, 0, 8) == 0
+
+
+def test_tensor_core_launch_plan_for_the_baseline_shapes(ured):
+    """The work-item rule of the tensor-core kernel: whole clouds per item when that keeps the 148 persistent CTAs
+    busy, smaller query groups for small batches, candidate ranges of 2048 for large clouds."""
+    import ctypes
+    lib = ured._native.load()
+
+    def plan(B, n1, n2, flags=0):
+        v, q, t, ns, items, split = (ctypes.c_int() for _ in range(6))
+        assert lib.ured_nn_launch_shape(B, n1, n2, flags, ctypes.byref(v), ctypes.byref(q), ctypes.byref(t), ctypes.byref(ns),
+                                        ctypes.byref(items), ctypes.byref(split)) == 0
+        return v.value, q.value, t.value, ns.value, items.value, split.value
+
+    assert plan(32, 2048, 2048) == (100, 1024, 448, 1, 128, 0)        # cfg1: 8 query tiles per item, one round of 128 items
+    assert plan(640, 2048, 2048) == (100, 2048, 448, 1, 1280, 0)      # cfg2: a whole cloud per item
+    assert plan(16, 16384, 16384) == (100, 2048, 448, 8, 256, 0)      # cfg4: 16 tiles per item, eight candidate ranges each
+    assert plan(125, 2048, 2048)[4] == 250                            # one cfg3 shard of an 8-GPU run
+    assert plan(1, 2048, 2048)[1:5] == (128, 448, 1, 32)              # one pair: every query tile its own item
+    one_dir = plan(3, 700, 3072, ured._native.URED_FLAG_ONE_DIRECTION)
+    assert one_dir[0] == 100 and one_dir[3] == 2 and one_dir[4] == 3 * -(-(-(-700 // 128)) // (one_dir[1] // 128))
+    assert plan(640, 2048, 2048, ured._native.URED_FLAG_FP32_SCREEN)[0] == 0 and plan(640, 2048, 2048, ured._native.URED_FLAG_EXACT_ONLY)[0] == 0
